@@ -1,0 +1,148 @@
+/* rt_cuda.h — C-ABI of the B200 trace loop (librt_cuda.so).
+ *
+ * Drop-in boundary for raytracer-gamma's render call.  Each entry point replaces
+ * a piece of the reference's OpenCL plumbing in main.cpp (paths relative to
+ * /root/reference/raytracer_gamma/); INTEGRATION.md shows the edited main().
+ *
+ *   rt_cuda_init            main.cpp:182-230  platform/device pick, context, queue
+ *                           (+ device_info.cpp:30-125 via rt_cuda_device_info)
+ *   rt_cuda_upload_scene    main.cpp:277-294  clCreateBuffer x2 + clEnqueueWriteBuffer x2
+ *   rt_cuda_render          main.cpp:339-362  clSetKernelArg 0-10 + clEnqueueNDRangeKernel + clFinish
+ *                           of `__kernel raytrace` (raytrace_kernel.cl:870-973); same result as the
+ *                           CPU loop main.cpp:404-453 around rayTrace() (raytracer.h:410)
+ *   rt_cuda_readback        main.cpp:456-471  clEnqueueReadBuffer + maxColourValuePixelBuffer (algebra.h:68)
+ *   rt_cuda_readback_rgb8   main.cpp:71-76    the quantiser of savePPM, on the device
+ *   rt_cuda_destroy         main.cpp:483-489  clRelease*
+ *   rt_cuda_strerror        err_code.h:31-140 err_code()
+ *
+ * Conventions: plain pointers and sizes only; the caller owns every host
+ * pointer; the library owns all device memory until rt_cuda_destroy; every call
+ * returns RT_CUDA_OK (0) or a negative rt_cuda_status and never exits the
+ * process (the reference's checkError prints and exits, err_code.h:142-155 —
+ * that stays the host program's choice).  Calls on one context must come from
+ * one thread at a time.  There is no CPU fallback: without a CUDA device
+ * rt_cuda_init fails with RT_CUDA_ERR_NO_DEVICE.
+ */
+#ifndef RT_CUDA_H
+#define RT_CUDA_H
+
+#include <stddef.h>
+#include <stdint.h>
+#include "rt_types.h"
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct rt_cuda_ctx rt_cuda_ctx;
+
+typedef enum rt_cuda_status {
+  RT_CUDA_OK = 0,
+  RT_CUDA_ERR_INVALID_ARG = -1,
+  RT_CUDA_ERR_NO_DEVICE = -2,
+  RT_CUDA_ERR_CUDA = -3,          /* a CUDA runtime call failed; see rt_cuda_last_error */
+  RT_CUDA_ERR_NO_SCENE = -4,
+  RT_CUDA_ERR_NO_FRAME = -5,
+  RT_CUDA_ERR_TOO_LARGE = -6,
+  RT_CUDA_ERR_OUT_OF_MEMORY = -7
+} rt_cuda_status;
+
+/* Limits of this implementation */
+#define RT_CUDA_MAX_SPHERES 12288u   /* filter records must fit one SM's shared memory */
+#define RT_CUDA_MAX_STACK   16       /* RTSTACK_MAXSIZE values accepted by rt_cuda_render */
+
+/* Counters and timings of the last render (device-side tallies). */
+typedef struct rt_cuda_stats {
+  uint64_t rays;            /* calcIntersection calls of the reference algorithm (raytracer.h:145) */
+  uint64_t shadow_rays;     /* of which shadow rays (raytracer.h:272)                               */
+  uint64_t contain_queries; /* primaryContainer calls (raytracer.h:245)                             */
+  uint64_t contain_tests;   /* its loop iterations, counted as the reference executes them          */
+  uint64_t exact_tests;     /* candidates that went through the exact expressions                   */
+  uint64_t samples;         /* rayTrace calls (main.cpp:439)                                        */
+  uint64_t lane_iters;      /* sphere-loop passes x 32 lanes                                        */
+  uint64_t active_lane_iters; /* of which lanes that carried a query                                */
+  uint64_t filter_tests;    /* discriminant filter tests executed = lane_iters * padded sphere count */
+  uint64_t null_rays;       /* rays with direction 0 (total internal reflection): certain miss, no sphere loop */
+  uint32_t sph_num, sph_padded, lgt_num;
+  uint32_t width, height, local_rows;
+  float    kernel_ms;       /* trace kernel only, CUDA events on the context's stream               */
+  float    max_colour;      /* NaN-skipping max of this context's rows, 0 if all black              */
+  uint32_t kernel_launches; /* kernels this library launched since the last render began            */
+  uint32_t grid, block, smem_bytes, staging;   /* launch shape; staging 1 = __constant__, 2 = shared via TMA bulk */
+} rt_cuda_stats;
+
+/* Open device `device` (cudaSetDevice ordinal).  *out receives the context. */
+int rt_cuda_init(int device, rt_cuda_ctx** out);
+
+/* Copy the scene (reference AoS layout) to the device and build the kernel's SoA
+ * form.  sphNum may be 0 (everything misses); lgtNum may be 0. */
+int rt_cuda_upload_scene(rt_cuda_ctx* ctx, const rt_sphere* spheres, unsigned sphNum,
+                         const rt_light* lights, unsigned lgtNum);
+
+/* Render the whole width x height frame.  zoom = kZoom, aliasFactor =
+ * kAliasFactor (raytrace_kernel.cl:876-877); maxStack = RTSTACK_MAXSIZE
+ * (raytraceStack.h:10; 6 in the reference CPU build, 5 in the OpenCL kernel).
+ * Asynchronous on the context's stream. */
+int rt_cuda_render(rt_cuda_ctx* ctx, unsigned width, unsigned height, float zoom,
+                   float aliasFactor, int maxStack);
+
+/* Render only the rows r with (r / stripRows) % stripStride == stripFirst — the
+ * row-strip shard of one GPU.  The context's framebuffer then holds those rows
+ * packed in increasing r. */
+int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned height, float zoom,
+                          float aliasFactor, int maxStack, unsigned stripRows,
+                          unsigned stripFirst, unsigned stripStride);
+
+/* Wait for the render, copy the float RGB rows (12 B per pixel, the
+ * reference's `Vec dst[]`) into dst, and return the NaN-skipping maximum
+ * (algebra.h:68-91; 1 when all black) in *outMax if non-NULL. */
+int rt_cuda_readback(rt_cuda_ctx* ctx, rt_vec* dst, float* outMax);
+
+/* Quantise on the device exactly as savePPM does (main.cpp:71-76) and copy 3
+ * bytes per pixel into dst.  maxColour <= 0 uses this context's own maximum. */
+int rt_cuda_readback_rgb8(rt_cuda_ctx* ctx, unsigned char* dst, float maxColour);
+
+/* Device-side quantise only (result stays in rt_cuda_device_rgb8). */
+int rt_cuda_quantise(rt_cuda_ctx* ctx, float maxColour);
+
+/* Device pointers for multi-GPU plumbing (NCCL gather / max all-reduce). */
+void* rt_cuda_device_packed(rt_cuda_ctx* ctx);   /* float[localRows*W*3], valid after rt_cuda_pack   */
+void* rt_cuda_device_rgb8(rt_cuda_ctx* ctx);     /* uint8[localRows*W*3], valid after rt_cuda_quantise */
+void* rt_cuda_device_max(rt_cuda_ctx* ctx);      /* one float (bits), 0 if black                     */
+int   rt_cuda_pack(rt_cuda_ctx* ctx);            /* float4 framebuffer -> packed float RGB on device */
+
+/* Use an existing cudaStream_t (e.g. the framework's current stream). */
+int rt_cuda_set_stream(rt_cuda_ctx* ctx, void* cudaStream);
+int rt_cuda_synchronize(rt_cuda_ctx* ctx);
+
+/* Tuning / debug switches: "staging" 0 auto | 1 __constant__ | 2 shared (TMA bulk);
+ * "no_filter" 1 = exact test against every sphere; "blocks_per_sm" 0 auto. */
+int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value);
+
+int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out);
+
+/* Multi-GPU assembly on the context's stream: `gathered` (device) holds nShards blocks of
+ * shardPitchBytes, block g = the RGB8 rows of shard g (rt_cuda_render_strips with
+ * stripFirst = g, stripStride = nShards) packed in increasing row order, e.g. the output
+ * of an NCCL all-gather.  Writes the height x width x 3 frame to `out` (device). */
+int rt_cuda_assemble_rgb8(rt_cuda_ctx* ctx, const void* gathered, void* out, unsigned width,
+                          unsigned height, unsigned stripRows, unsigned nShards,
+                          size_t shardPitchBytes);
+
+/* Measure the FP32 FMA ceiling of this device (register-only FFMA chains), in TFLOP/s:
+ * the empirical denominator beside the nominal #SM x 128 x 2 x clock. */
+int rt_cuda_ffma_peak(rt_cuda_ctx* ctx, int iters, float* outTflops);
+
+void rt_cuda_destroy(rt_cuda_ctx* ctx);
+
+const char* rt_cuda_strerror(int status);
+const char* rt_cuda_last_error(rt_cuda_ctx* ctx);   /* text of the last CUDA failure */
+
+int rt_cuda_device_count(void);
+/* One-paragraph description of a device (the analogue of output_device_info). */
+int rt_cuda_device_info(int device, char* buf, size_t bufSize);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* RT_CUDA_H */

@@ -1,0 +1,300 @@
+"""raytracer-gamma trace loop, B200-native — thin Python binding over the C-ABI.
+
+The product is ``librt_cuda.so`` (``csrc/rt_shim.cu`` + ``csrc/rt_kernels.cuh``,
+declared in ``include/rt_cuda.h``); this module only loads it with ctypes so that
+tests, ``bench.py`` and the multi-GPU driver can call it.  There is no CPU
+rendering path here: if the library is missing or no B200 is present the calls
+raise.
+
+The directory name contains a hyphen, so import it through
+``__graft_entry__.load_package()`` (registers it as ``raytracer_gamma_b200``).
+"""
+from __future__ import annotations
+
+import ctypes
+import os
+import subprocess
+from pathlib import Path
+
+import numpy as np
+
+PKG_DIR = Path(__file__).resolve().parent
+REPO_ROOT = PKG_DIR.parent
+LIB_PATH = PKG_DIR / "librt_cuda.so"
+HOST_BIN = PKG_DIR / "rt_gamma"
+
+# Layout of the reference PODs (sphere.h:9-14, raytracer.h:20-25, vec.h:27-29)
+SPHERE_DTYPE = np.dtype(
+    [("pos", "<f4", 3), ("radius", "<f4"), ("matte", "<f4", 3), ("gloss", "<f4", 3),
+     ("opacity", "<f4"), ("refractiveIndex", "<f4")])
+LIGHT_DTYPE = np.dtype([("pos", "<f4", 3), ("col", "<f4", 3)])
+assert SPHERE_DTYPE.itemsize == 48 and LIGHT_DTYPE.itemsize == 24
+
+NVCC_FLAGS = [
+    "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false",
+    "-Xcompiler", "-fPIC,-ffp-contract=off", "-std=c++17",
+]
+
+
+def build(force: bool = False, verbose: bool = False) -> Path:
+    """Compile librt_cuda.so (and the C++ host program) in-tree for sm_100a."""
+    srcs = [PKG_DIR / "csrc" / "rt_shim.cu", PKG_DIR / "host" / "rt_scene.c"]
+    deps = srcs + list((PKG_DIR / "csrc").glob("*.cuh")) + list((PKG_DIR / "csrc").glob("*.h")) + \
+        list((REPO_ROOT / "include").glob("*.h"))
+    newest = max(p.stat().st_mtime for p in deps)
+    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
+        cmd = ["nvcc", *NVCC_FLAGS, "-shared", f"-I{REPO_ROOT / 'include'}", f"-I{PKG_DIR / 'csrc'}",
+               "-o", str(LIB_PATH), *map(str, srcs)]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    host_src = PKG_DIR / "host" / "main.cpp"
+    if host_src.exists() and (force or not HOST_BIN.exists()
+                              or HOST_BIN.stat().st_mtime < max(newest, host_src.stat().st_mtime)):
+        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", f"-I{REPO_ROOT / 'include'}",
+               "-o", str(HOST_BIN), str(host_src), f"-L{PKG_DIR}", "-lrt_cuda",
+               f"-Wl,-rpath,{PKG_DIR}", "-Wl,-rpath,$ORIGIN"]
+        if verbose:
+            print(" ".join(cmd))
+        subprocess.run(cmd, check=True)
+    return LIB_PATH
+
+
+class RtCudaError(RuntimeError):
+    def __init__(self, status: int, where: str, detail: str = ""):
+        self.status = status
+        name = _lib().rt_cuda_strerror(status).decode()
+        super().__init__(f"{where}: {name} ({status}) {detail}".strip())
+
+
+class Stats(ctypes.Structure):
+    _fields_ = [
+        ("rays", ctypes.c_uint64), ("shadow_rays", ctypes.c_uint64),
+        ("contain_queries", ctypes.c_uint64), ("contain_tests", ctypes.c_uint64),
+        ("exact_tests", ctypes.c_uint64), ("samples", ctypes.c_uint64),
+        ("lane_iters", ctypes.c_uint64), ("active_lane_iters", ctypes.c_uint64),
+        ("filter_tests", ctypes.c_uint64), ("null_rays", ctypes.c_uint64),
+        ("sph_num", ctypes.c_uint32), ("sph_padded", ctypes.c_uint32), ("lgt_num", ctypes.c_uint32),
+        ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("local_rows", ctypes.c_uint32),
+        ("kernel_ms", ctypes.c_float), ("max_colour", ctypes.c_float),
+        ("kernel_launches", ctypes.c_uint32),
+        ("grid", ctypes.c_uint32), ("block", ctypes.c_uint32), ("smem_bytes", ctypes.c_uint32),
+        ("staging", ctypes.c_uint32),
+    ]
+
+    def as_dict(self) -> dict:
+        return {k: getattr(self, k) for k, _ in self._fields_}
+
+
+# Every symbol include/rt_cuda.h and include/rt_scene.h declare: (name, restype, argtypes)
+_P = ctypes.c_void_p
+C_ABI = [
+    ("rt_cuda_init", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(_P)]),
+    ("rt_cuda_upload_scene", ctypes.c_int, [_P, _P, ctypes.c_uint, _P, ctypes.c_uint]),
+    ("rt_cuda_render", ctypes.c_int,
+     [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_float, ctypes.c_float, ctypes.c_int]),
+    ("rt_cuda_render_strips", ctypes.c_int,
+     [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_float, ctypes.c_float, ctypes.c_int,
+      ctypes.c_uint, ctypes.c_uint, ctypes.c_uint]),
+    ("rt_cuda_readback", ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_float)]),
+    ("rt_cuda_readback_rgb8", ctypes.c_int, [_P, _P, ctypes.c_float]),
+    ("rt_cuda_quantise", ctypes.c_int, [_P, ctypes.c_float]),
+    ("rt_cuda_device_packed", _P, [_P]),
+    ("rt_cuda_device_rgb8", _P, [_P]),
+    ("rt_cuda_device_max", _P, [_P]),
+    ("rt_cuda_pack", ctypes.c_int, [_P]),
+    ("rt_cuda_set_stream", ctypes.c_int, [_P, _P]),
+    ("rt_cuda_synchronize", ctypes.c_int, [_P]),
+    ("rt_cuda_set_option", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_long]),
+    ("rt_cuda_get_stats", ctypes.c_int, [_P, ctypes.POINTER(Stats)]),
+    ("rt_cuda_assemble_rgb8", ctypes.c_int,
+     [_P, _P, _P, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_uint, ctypes.c_size_t]),
+    ("rt_cuda_ffma_peak", ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+    ("rt_cuda_destroy", None, [_P]),
+    ("rt_cuda_strerror", ctypes.c_char_p, [ctypes.c_int]),
+    ("rt_cuda_last_error", ctypes.c_char_p, [_P]),
+    ("rt_cuda_device_count", ctypes.c_int, []),
+    ("rt_cuda_device_info", ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
+    ("rt_make_material", None,
+     [_P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
+    ("rt_scene_default", None, [_P, _P]),
+    ("rt_scene_synth", ctypes.c_int, [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint64, _P, _P]),
+]
+
+_LIB = None
+
+
+def _lib() -> ctypes.CDLL:
+    global _LIB
+    if _LIB is None:
+        if not LIB_PATH.exists():
+            raise FileNotFoundError(
+                f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+                "There is no CPU fallback for the trace loop.")
+        lib = ctypes.CDLL(str(LIB_PATH))
+        for name, res, args in C_ABI:
+            fn = getattr(lib, name)
+            fn.restype = res
+            fn.argtypes = args
+        _LIB = lib
+    return _LIB
+
+
+def load() -> ctypes.CDLL:
+    return _lib()
+
+
+def device_count() -> int:
+    return _lib().rt_cuda_device_count()
+
+
+def device_info(device: int = 0) -> str:
+    buf = ctypes.create_string_buffer(512)
+    rc = _lib().rt_cuda_device_info(device, buf, len(buf))
+    if rc:
+        raise RtCudaError(rc, "rt_cuda_device_info")
+    return buf.value.decode()
+
+
+# ---- scenes (host side, include/rt_scene.h) ---------------------------------
+def default_scene():
+    """The scene literal of main.cpp:113-168 as (spheres, lights) structured arrays."""
+    sph = np.zeros(3, SPHERE_DTYPE)
+    lgt = np.zeros(2, LIGHT_DTYPE)
+    _lib().rt_scene_default(sph.ctypes.data, lgt.ctypes.data)
+    return sph, lgt
+
+
+def synth_scene(n: int, lights: int = 4, seed: int = 0):
+    """synth(N, L, seed) of SURVEY.md §8(d)."""
+    sph = np.zeros(n, SPHERE_DTYPE)
+    lgt = np.zeros(lights, LIGHT_DTYPE)
+    rc = _lib().rt_scene_synth(n, lights, seed, sph.ctypes.data, lgt.ctypes.data)
+    if rc:
+        raise ValueError("rt_scene_synth: bad arguments")
+    return sph, lgt
+
+
+def make_material(matte, gloss, opacity, gloss_factor, refractive_index) -> np.ndarray:
+    out = np.zeros(8, np.float32)
+    m = np.asarray(matte, np.float32)
+    g = np.asarray(gloss, np.float32)
+    _lib().rt_make_material(out.ctypes.data, m.ctypes.data, g.ctypes.data, opacity, gloss_factor,
+                            refractive_index)
+    return out
+
+
+def local_rows(height: int, strip_rows: int, first: int, stride: int) -> np.ndarray:
+    """Global row numbers, in storage order, of the shard (first, stride) of a strip-interleaved frame."""
+    rows = np.arange(height)
+    return rows[(rows // strip_rows) % stride == first]
+
+
+class Renderer:
+    """One context of the C-ABI (one GPU).  Mirrors the call sequence of the
+    reference's main(): init -> upload_scene -> render -> readback."""
+
+    def __init__(self, device: int = 0):
+        self._lib = _lib()
+        self._ctx = _P()
+        rc = self._lib.rt_cuda_init(device, ctypes.byref(self._ctx))
+        if rc:
+            raise RtCudaError(rc, "rt_cuda_init")
+        self.device = device
+        self.width = self.height = self.rows = 0
+
+    def _check(self, rc: int, where: str):
+        if rc:
+            raise RtCudaError(rc, where, self._lib.rt_cuda_last_error(self._ctx).decode())
+
+    def close(self):
+        if self._ctx:
+            self._lib.rt_cuda_destroy(self._ctx)
+            self._ctx = _P()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def set_option(self, key: str, value: int):
+        self._check(self._lib.rt_cuda_set_option(self._ctx, key.encode(), int(value)), "rt_cuda_set_option")
+
+    def set_stream(self, cuda_stream: int):
+        self._check(self._lib.rt_cuda_set_stream(self._ctx, _P(cuda_stream)), "rt_cuda_set_stream")
+
+    def upload_scene(self, spheres: np.ndarray, lights: np.ndarray):
+        spheres = np.ascontiguousarray(spheres)
+        lights = np.ascontiguousarray(lights)
+        assert spheres.dtype.itemsize == 48 or spheres.size == 0
+        assert lights.dtype.itemsize == 24 or lights.size == 0
+        self._check(self._lib.rt_cuda_upload_scene(
+            self._ctx, spheres.ctypes.data if len(spheres) else None, len(spheres),
+            lights.ctypes.data if len(lights) else None, len(lights)), "rt_cuda_upload_scene")
+
+    def render(self, width: int, height: int, zoom: float = -4.0, alias: float = 1.0, max_stack: int = 6):
+        self._check(self._lib.rt_cuda_render(self._ctx, width, height, zoom, alias, max_stack), "rt_cuda_render")
+        self.width, self.height, self.rows = width, height, height
+
+    def render_strips(self, width, height, zoom, alias, max_stack, strip_rows, first, stride):
+        self._check(self._lib.rt_cuda_render_strips(self._ctx, width, height, zoom, alias, max_stack,
+                                                    strip_rows, first, stride), "rt_cuda_render_strips")
+        self.width, self.height = width, height
+        self.rows = len(local_rows(height, strip_rows, first, stride))
+
+    def readback(self, out: np.ndarray | None = None):
+        """-> (float32 [rows, W, 3], max colour)"""
+        if out is None:
+            out = np.empty((self.rows, self.width, 3), np.float32)
+        mx = ctypes.c_float(0)
+        self._check(self._lib.rt_cuda_readback(self._ctx, out.ctypes.data, ctypes.byref(mx)), "rt_cuda_readback")
+        return out, mx.value
+
+    def readback_rgb8(self, max_colour: float = 0.0, out: np.ndarray | None = None) -> np.ndarray:
+        if out is None:
+            out = np.empty((self.rows, self.width, 3), np.uint8)
+        self._check(self._lib.rt_cuda_readback_rgb8(self._ctx, out.ctypes.data, max_colour), "rt_cuda_readback_rgb8")
+        return out
+
+    def quantise(self, max_colour: float = 0.0):
+        self._check(self._lib.rt_cuda_quantise(self._ctx, max_colour), "rt_cuda_quantise")
+
+    def pack(self):
+        self._check(self._lib.rt_cuda_pack(self._ctx), "rt_cuda_pack")
+
+    def synchronize(self):
+        self._check(self._lib.rt_cuda_synchronize(self._ctx), "rt_cuda_synchronize")
+
+    def stats(self) -> dict:
+        s = Stats()
+        self._check(self._lib.rt_cuda_get_stats(self._ctx, ctypes.byref(s)), "rt_cuda_get_stats")
+        return s.as_dict()
+
+    def assemble_rgb8(self, gathered_ptr: int, out_ptr: int, width, height, strip_rows, shards, pitch):
+        self._check(self._lib.rt_cuda_assemble_rgb8(self._ctx, _P(gathered_ptr), _P(out_ptr), width, height,
+                                                    strip_rows, shards, pitch), "rt_cuda_assemble_rgb8")
+
+    def ffma_peak(self, iters: int = 4096) -> float:
+        t = ctypes.c_float(0)
+        self._check(self._lib.rt_cuda_ffma_peak(self._ctx, iters, ctypes.byref(t)), "rt_cuda_ffma_peak")
+        return t.value
+
+    def device_ptr(self, which: str) -> int:
+        fn = {"packed": self._lib.rt_cuda_device_packed, "rgb8": self._lib.rt_cuda_device_rgb8,
+              "max": self._lib.rt_cuda_device_max}[which]
+        return int(fn(self._ctx) or 0)
+
+
+def write_ppm(path, rgb8: np.ndarray):
+    """Binary P6 with the reference's header (main.cpp:66)."""
+    h, w, _ = rgb8.shape
+    with open(path, "wb") as f:
+        f.write(b"P6\n%d %d\n255\n" % (w, h))
+        f.write(np.ascontiguousarray(rgb8).tobytes())

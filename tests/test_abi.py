@@ -1,0 +1,79 @@
+"""CPU tests of the drop-in boundary: the C-ABI library builds, loads, exports every
+symbol the headers declare, and refuses to work without a GPU (no CPU fallback)."""
+import ctypes
+import re
+import subprocess
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+ROOT = Path(__file__).resolve().parent.parent
+
+
+def _declared(header: str):
+    text = (ROOT / "include" / header).read_text()
+    text = re.sub(r"/\*.*?\*/", "", text, flags=re.S)
+    return sorted(set(re.findall(r"\b(rt_(?:cuda|scene|make)_\w+)\s*\(", text)))
+
+
+def test_library_exports_every_declared_symbol(pkg):
+    lib = ctypes.CDLL(str(pkg.LIB_PATH))
+    names = _declared("rt_cuda.h") + _declared("rt_scene.h")
+    assert len(names) >= 22
+    for n in names:
+        assert hasattr(lib, n), f"{n} declared in include/ but not exported"
+    # and the binding covers them all
+    bound = {n for n, _, _ in pkg.C_ABI}
+    assert set(names) <= bound, set(names) - bound
+
+
+def test_signatures_are_plain_c(pkg):
+    """extern "C", plain pointers and sizes: no mangled or torch symbols in the dynamic table."""
+    out = subprocess.run(["nm", "-D", "--defined-only", str(pkg.LIB_PATH)], capture_output=True, text=True).stdout
+    exported = [l.split()[-1] for l in out.splitlines() if " T " in l]
+    assert all(not s.startswith("_Z") or "rtg" in s for s in exported if s.startswith("rt_"))
+    assert "rt_cuda_render" in exported and "rt_cuda_readback" in exported
+    assert not any("torch" in s or "at::" in s for s in exported)
+
+
+def test_pod_layouts(pkg):
+    assert pkg.SPHERE_DTYPE.itemsize == 48 and pkg.LIGHT_DTYPE.itemsize == 24
+    assert pkg.SPHERE_DTYPE.fields["radius"][1] == 12 and pkg.SPHERE_DTYPE.fields["opacity"][1] == 40
+    assert ctypes.sizeof(pkg.Stats) % 8 == 0
+
+
+def test_strerror(pkg):
+    lib = pkg.load()
+    assert lib.rt_cuda_strerror(0) == b"RT_CUDA_OK"
+    assert lib.rt_cuda_strerror(-2) == b"RT_CUDA_ERR_NO_DEVICE"
+    assert lib.rt_cuda_strerror(-99) == b"RT_CUDA_ERR_UNKNOWN"
+
+
+def test_no_cpu_fallback_without_a_gpu(pkg):
+    """On a machine without a CUDA device init must fail loudly, never render on the CPU."""
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.RtCudaError) as e:
+        pkg.Renderer(0)
+    assert e.value.status == -2
+    lib = pkg.load()
+    assert lib.rt_cuda_render(None, 8, 8, -4.0, 1.0, 6) == -1       # null context: invalid argument
+    assert lib.rt_cuda_readback(None, None, None) == -1
+
+
+def test_product_sources_do_not_touch_the_oracle():
+    """Only tests/, smoke() and bench.py's CPU legs may use oracle/."""
+    for p in (ROOT / "raytracer-gamma_b200").rglob("*"):
+        if p.suffix in (".py", ".cu", ".cuh", ".h", ".c", ".cpp"):
+            text = p.read_text()
+            assert "rt_oracle" not in text and "oracle/" not in text and "hostsim" not in text.replace(
+                "tests/hostsim.cpp", ""), p
+
+
+def test_local_rows_partition(pkg):
+    H = 37
+    for G in (1, 2, 3, 4, 8):
+        rows = [pkg.local_rows(H, 4, g, G) for g in range(G)]
+        allr = np.sort(np.concatenate(rows))
+        assert np.array_equal(allr, np.arange(H))

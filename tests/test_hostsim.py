@@ -1,0 +1,87 @@
+"""CPU tests of the kernel's state machine (rt_core.cuh) through the lane simulator
+(tests/hostsim.cpp): same machine, same filter, same exact tests as the CUDA kernel,
+run one lane at a time and compared bit-for-bit with the oracle."""
+import json
+from pathlib import Path
+
+import numpy as np
+import pytest
+
+GOLD = Path(__file__).resolve().parent / "golden"
+FACTS = json.loads((GOLD / "facts.json").read_text())
+G = np.load(GOLD / "golden.npz")
+FB_CASES = [k for k in FACTS if "W" in FACTS[k]]
+
+
+def _case_scene(pkg, case):
+    name = case.split("_")[0]
+    sph = np.ascontiguousarray(G[f"{name}_spheres"]).view(pkg.SPHERE_DTYPE).reshape(-1)
+    lgt = np.ascontiguousarray(G[f"{name}_lights"]).view(pkg.LIGHT_DTYPE).reshape(-1)
+    return sph, lgt
+
+
+@pytest.mark.parametrize("case", FB_CASES)
+def test_machine_matches_golden(pkg, orc_mod, hostsim, case):
+    f = FACTS[case]
+    sph, lgt = _case_scene(pkg, case)
+    fb, _ = hostsim(sph, lgt, f["W"], f["H"], f["zoom"], f["alias"], f["S"])
+    assert np.array_equal(orc_mod.canon(fb), G[case])
+
+
+@pytest.mark.parametrize("S", [1, 2, 5, 6, 8, 12])
+def test_machine_matches_oracle_counters_and_pixels(pkg, orc_mod, oracle, hostsim, S):
+    """Work counters are the reference algorithm's: rays, shadow rays, container queries/tests."""
+    sph, lgt = pkg.default_scene()
+    a, ca = oracle.render(sph, lgt, 200, 150, -4.0, 3.0, S)
+    b, cb = hostsim(sph, lgt, 200, 150, -4.0, 3.0, S)
+    assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b))
+    for k in ("rays", "shadow_rays", "contain_queries", "contain_tests", "samples"):
+        assert ca[k] == cb[k], k
+
+
+def test_filter_never_changes_the_image(pkg, orc_mod, hostsim):
+    """The FMA filter only removes certain misses: with it off (exact test against every
+    sphere) the framebuffer is the same, and far fewer exact tests are needed with it on."""
+    for n, seed in [(64, 0), (300, 5)]:
+        sph, lgt = pkg.synth_scene(n, 4, seed=seed)
+        a, ca = hostsim(sph, lgt, 96, 64, -4.0, 1.0, 8)
+        b, cb = hostsim(sph, lgt, 96, 64, -4.0, 1.0, 8, no_filter=True)
+        assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b))
+        assert ca["rays"] == cb["rays"]
+        assert ca["exact_tests"] < cb["exact_tests"] / 20
+
+
+def test_machine_matches_oracle_synthetic(pkg, orc_mod, oracle, hostsim):
+    for n, l, seed, W, H, alias, S in [(256, 4, 0, 120, 68, 2.0, 8), (1024, 4, 0, 64, 36, 1.0, 8),
+                                       (17, 1, 9, 57, 33, 1.0, 4), (33, 0, 2, 40, 30, 1.0, 6)]:
+        sph, lgt = pkg.synth_scene(n, l, seed=seed)
+        a, ca = oracle.render(sph, lgt, W, H, -4.0, alias, S)
+        b, cb = hostsim(sph, lgt, W, H, -4.0, alias, S)
+        assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), (n, l, seed)
+        assert ca["rays"] == cb["rays"] and ca["contain_tests"] == cb["contain_tests"]
+
+
+def test_machine_edge_cases(pkg, orc_mod, oracle, hostsim):
+    sph, lgt = pkg.default_scene()
+    # fractional / sub-unit alias factors change the sample count (int i < float alias)
+    for alias in (0.5, 1.5, 2.5):
+        a, _ = oracle.render(sph, lgt, 40, 30, -4.0, alias, 6)
+        b, _ = hostsim(sph, lgt, 40, 30, -4.0, alias, 6)
+        assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), alias
+    # empty scene: every ray misses, the image is black
+    b, cb = hostsim(sph[:0], lgt, 16, 12, -4.0, 1.0, 6)
+    assert not b.any() and cb["rays"] == 16 * 12
+    # far spheres beyond kMaxRenderDist = 1000 are ignored (raytracer.h:156)
+    far = sph.copy()
+    far["pos"][:, 2] -= 1200
+    a, _ = oracle.render(far, lgt, 32, 24, -4.0, 1.0, 6)
+    b, _ = hostsim(far, lgt, 32, 24, -4.0, 1.0, 6)
+    assert np.array_equal(a, b) and not a.any()
+    # camera inside a sphere, overlapping spheres (container order matters, raytracer.h:264)
+    inside = sph.copy()
+    inside["pos"][0] = (0, 0, -1)
+    inside["radius"][0] = 3
+    inside["pos"][1] = (0.5, 0, -2)
+    a, _ = oracle.render(inside, lgt, 48, 36, -4.0, 1.0, 6)
+    b, _ = hostsim(inside, lgt, 48, 36, -4.0, 1.0, 6)
+    assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b))
