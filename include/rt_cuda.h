@@ -116,7 +116,8 @@ int rt_cuda_set_stream(rt_cuda_ctx* ctx, void* cudaStream);
 int rt_cuda_synchronize(rt_cuda_ctx* ctx);
 
 /* Tuning / debug switches: "staging" 0 auto | 1 __constant__ | 2 shared (TMA bulk);
- * "no_filter" 1 = exact test against every sphere; "blocks_per_sm" 0 auto. */
+ * "no_filter" 1 = exact test against every sphere; "blocks_per_sm" 0 auto;
+ * "min_blocks" 0 auto | 2 | 3 | 4 = register-budget variant of the trace kernel. */
 int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value);
 
 int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out);

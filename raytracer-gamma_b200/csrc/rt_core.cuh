@@ -173,25 +173,29 @@ RT_HD bool filter_pass(const Query& qy, float4_ s) {
 }
 
 /* ---- exact per-candidate tests --------------------------------------------- */
-/* raytracer.h:81-141 */
+/* raytracer.h:81-141.  The reference forms both roots u0 = (-b+root)/denom and
+ * u1 = (-b-root)/denom and keeps the smallest one in (1e-5, 10000).  Rounding is
+ * monotonic and denom = 2 d.d > 0, so u1 <= u0 always: when u1 > 1e-5 it is the
+ * answer (or, if u1 >= 10000, so is u0 and there is none) and u0 need not be
+ * divided out; u0 is only formed when u1 fails the lower bound (or is NaN).
+ * Same decisions, same t, one IEEE division less on the common path. */
 RT_HD bool ray_sphere_exact(float4_ g, V3 o, V3 d, float& t) {
   const V3 disp = vsub(o, mk(g.x, g.y, g.z));
   const float a = vdot(d, d);
   const float b = ex_mul(2.0f, vdot(d, disp));
   const float c = ex_sub(vdot(disp, disp), ex_mul(g.w, g.w));
   const float radicand = ex_sub(ex_mul(b, b), ex_mul(ex_mul(4.0f, a), c));
-  bool ok = false;
-  if (radicand >= 0.0f) {
-    const float root = ex_sqrt(radicand);
-    const float denom = ex_mul(2.0f, a);
-    const float u0 = ex_div(ex_add(-b, root), denom);
-    const float u1 = ex_div(ex_sub(-b, root), denom);
-    float best = 10000.f;
-    if (u0 > 1.0e-5f && u0 < best) { best = u0; ok = true; }
-    if (u1 > 1.0e-5f && u1 < best) { best = u1; ok = true; }
-    t = best;
+  if (!(radicand >= 0.0f)) return false;
+  const float root = ex_sqrt(radicand);
+  const float denom = ex_mul(2.0f, a);
+  const float u1 = ex_div(ex_sub(-b, root), denom);
+  if (u1 > 1.0e-5f) {
+    if (u1 < 10000.f) { t = u1; return true; }
+    return false;
   }
-  return ok;
+  const float u0 = ex_div(ex_add(-b, root), denom);
+  if (u0 > 1.0e-5f && u0 < 10000.f) { t = u0; return true; }
+  return false;
 }
 
 /* raytracer.h:259-266 */

@@ -98,8 +98,8 @@ __device__ __forceinline__ bool work_to_pixel(const TraceParams& p, uint32_t idx
   return true;
 }
 
-template <bool USE_CONST>
-__global__ void __launch_bounds__(RT_BLOCK, 2) trace_kernel(const TraceParams p) {
+template <bool USE_CONST, int MIN_BLOCKS>
+__global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const TraceParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists] */
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
@@ -204,6 +204,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 2) trace_kernel(const TraceParams p)
             mask &= mask - 1;
             if (cnt == RT_LIST_MAX) {
               /* list full: resolve what we have now (rare, divergent) */
+#pragma unroll 1
               for (int k = 0; k < RT_LIST_MAX; ++k)
                 resolve_candidate(L, p.sc, sList[k * RT_BLOCK + tid]);
               cnt = 0;
@@ -215,6 +216,7 @@ __global__ void __launch_bounds__(RT_BLOCK, 2) trace_kernel(const TraceParams p)
       }
       /* ---- resolve (convergent over lanes) ---- */
       const int maxc = __reduce_max_sync(FULL, cnt);
+#pragma unroll 1
       for (int k = 0; k < maxc; ++k) {
         if (k < cnt) resolve_candidate(L, p.sc, sList[k * RT_BLOCK + tid]);
       }

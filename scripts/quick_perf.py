@@ -13,7 +13,10 @@ cases = [
     ("synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {}),
     ("synth256 4K a1 s6 const", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"staging": 1}),
     ("synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {}),
-    ("synth1024 4K a1 s8 1blk", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"blocks_per_sm": 1}),
+    ("synth1024 4K a1 s8 mb3", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3}),
+    ("synth1024 4K a1 s8 mb4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4}),
+    ("synth256 4K a1 s6 mb3", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 3}),
+    ("synth256 4K a1 s6 mb4", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 4}),
     ("synth16 4K a1 s8", pkg.synth_scene(16, 4), 3840, 2160, 1.0, 8, {}),
     ("synth4096 2K a1 s8", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {}),
 ]
