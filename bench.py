@@ -265,9 +265,9 @@ def run_ours(args):
     r = pkg.Renderer(local_rank)
     stream = torch.cuda.Stream(device=dev)
     r.set_stream(stream.cuda_stream)
-    my_rows = pkg.local_rows(H, STRIP_ROWS, rank, G) if G > 1 else np.arange(H)
-    max_rows = max(len(pkg.local_rows(H, STRIP_ROWS, g, G)) for g in range(G)) if G > 1 else H
-    pitch = ((max_rows * W * 3 + 15) // 16) * 16
+    import importlib
+    par = importlib.import_module(pkg.__name__ + ".parallel")
+    my_rows = par.shard_rows(H, STRIP_ROWS, rank, G) if G > 1 else np.arange(H)
     flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
 
     r.upload_scene(sph, lgt)
@@ -286,8 +286,7 @@ def run_ours(args):
     rgb_local = torch.as_tensor(CudaArray(r.device_ptr("rgb8"), len(my_rows) * W * 3), device=dev)
     max_bits = torch.as_tensor(CudaArray(r.device_ptr("max"), 4, "<i4", 4), device=dev)
     if G > 1:
-        send = torch.zeros(pitch, dtype=torch.uint8, device=dev)
-        gathered = torch.empty(G * pitch, dtype=torch.uint8, device=dev)
+        xchg = par.StripExchange(dist, torch, H, W, STRIP_ROWS, rank, G, dev)
         frame = torch.empty(H * W * 3, dtype=torch.uint8, device=dev)
     host_frame = torch.empty(H * W * 3, dtype=torch.uint8).pin_memory() if rank == 0 else None
 
@@ -299,13 +298,12 @@ def run_ours(args):
         k = 1
         if G > 1:
             # global normalisation (algebra.h:68-91): max over shards; non-negative floats order as ints
-            dist.all_reduce(max_bits, op=dist.ReduceOp.MAX)
+            xchg.reduce_max(max_bits)
         r.quantise(0.0)
         k += 1
         if G > 1:
-            send[: rgb_local.numel()].copy_(rgb_local, non_blocking=True)
-            dist.all_gather_into_tensor(gathered, send)
-            r.assemble_rgb8(gathered.data_ptr(), frame.data_ptr(), W, H, STRIP_ROWS, G, pitch)
+            gathered = xchg.gather(rgb_local)
+            r.assemble_rgb8(gathered.data_ptr(), frame.data_ptr(), W, H, STRIP_ROWS, G, xchg.pitch)
             k += 1
         return k
 
