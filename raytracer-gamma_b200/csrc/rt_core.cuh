@@ -160,8 +160,12 @@ RT_HD void query_point(Query& qy, V3 p) {
 
 RT_HD V3 query_origin(const Query& qy) { return mk(-0.5f * qy.px, -0.5f * qy.py, -0.5f * qy.pz); }
 
-/* One filter test: true = this sphere may be hit / may contain the point. */
-RT_HD bool filter_pass(const Query& qy, float4_ s) {
+/* One filter test.  Returns lhs - ch: NEGATIVE (sign bit set) means certain miss; zero
+ * or positive means the sphere may be hit / may contain the point.  lhs and ch are finite
+ * or -inf/+inf by construction (null queries, padding), and the rounded difference of two
+ * such values carries the sign of the exact difference, so "sign bit set" <=> lhs < ch.
+ * Queries with NaN/inf geometry never reach the filter (query_filterable). */
+RT_HD float filter_diff(const Query& qy, float4_ s) {
   float bq = fast_fma(qy.ndx, s.x, qy.od);
   bq = fast_fma(qy.ndy, s.y, bq);
   bq = fast_fma(qy.ndz, s.z, bq);
@@ -169,7 +173,17 @@ RT_HD bool filter_pass(const Query& qy, float4_ s) {
   ch = fast_fma(qy.py, s.y, ch);
   ch = fast_fma(qy.pz, s.z, ch);
   const float lhs = fast_fma(bq, bq, -qy.q);
-  return !(lhs < ch);
+  return ex_sub(lhs, ch);
+}
+RT_HD bool filter_pass(const Query& qy, float4_ s) { return !(filter_diff(qy, s) < 0.f); }
+
+/* The sign-bit form of the filter is only conservative for non-NaN inputs.  A query whose
+ * numbers are not all finite (q = +inf marks a null query and is fine) skips the filter and
+ * is tested exactly against every sphere. */
+RT_HD bool finite_f(float x) { return fabsf(x) <= 3.402823466e+38f; }
+RT_HD bool query_filterable(const Query& qy) {
+  return finite_f(qy.ndx) && finite_f(qy.ndy) && finite_f(qy.ndz) && finite_f(qy.od) &&
+         finite_f(qy.px) && finite_f(qy.py) && finite_f(qy.pz) && !(qy.q != qy.q) && qy.q > -INFINITY;
 }
 
 /* ---- exact per-candidate tests --------------------------------------------- */
@@ -360,10 +374,14 @@ RT_HD float fresnel_term(float n1, float n2, float cosA1, float cosA2) {
   return refl;
 }
 
+/* What a handler leaves for the common tail of advance(): each tail (shadow set-up,
+ * matte/transparency step, unwinding) exists once, so lanes of different kinds
+ * re-converge on it and the code stays small. */
+enum { ACT_QUERY = 0, ACT_UNWIND = 1, ACT_SHADOW = 2, ACT_MATTE = 3, ACT_NOMATTE = 4 };
+
 /* After the containment probe: refraction (raytracer.h:642-815), suspend the
- * call (raytracer.h:516-522), launch the refracted child (raytracer.h:524-533).
- * Returns true when the sample is finished. */
-RT_HD bool after_contain(Lane& L, const SceneView& sc, Frame* stack, const Camera& cam) {
+ * call (raytracer.h:516-522), launch the refracted child (raytracer.h:524-533). */
+RT_HD int after_contain(Lane& L, const SceneView& sc, Frame* stack, const Camera& cam) {
   const int target = (L.hitIdx >= 0) ? L.hitIdx : (int)sc.n;
   const float4_ objA = sc.matA[L.obj], objB = sc.matB[L.obj];
   const float4_ medA = sc.matA[L.medium], medB = sc.matB[L.medium];
@@ -440,14 +458,13 @@ RT_HD bool after_contain(Lane& L, const SceneView& sc, Frame* stack, const Camer
     L.rayD = rdir; L.rayI = rint; L.medium = target;
     L.colour = mk(0.f, 0.f, 0.f);
     set_ray_query(L, K_TRACE, L.P, rdir);
-    return false;
+    return ACT_QUERY;
   }
-  return unwind(L, stack, cam);                          /* child push dropped */
+  return ACT_UNWIND;                                     /* child push dropped */
 }
 
 /* Matte term complete (raytracer.h:468-484), then transparency (raytracer.h:494). */
-RT_HD bool after_matte(Lane& L, const SceneView& sc, Frame* stack, const Camera& cam,
-                       bool haveMatte) {
+RT_HD int after_matte(Lane& L, const SceneView& sc, bool haveMatte) {
   const float4_ objA = sc.matA[L.obj];
   const float opacity = objA.w;
   if (haveMatte) {
@@ -463,41 +480,43 @@ RT_HD bool after_matte(Lane& L, const SceneView& sc, Frame* stack, const Camera&
     L.hitIdx = -1; L.minT = 1000.f;
     query_point(L.qy, probe);
     L.ctr.containQ++;
-    return false;
+    return ACT_QUERY;
   }
   L.result = L.colour;
-  return unwind(L, stack, cam);
+  return ACT_UNWIND;
 }
 
 /* Advance the lane after its query has been answered (L.hitIdx / L.minT).
  * Returns true when the lane's current SAMPLE is finished (L.result valid);
  * otherwise L.qy / L.kind hold the next query. */
 RT_HD bool advance(Lane& L, const SceneView& sc, Frame* stack, const Camera& cam) {
+  int act;
   if (L.kind == K_TRACE) {
     L.ctr.rays++;
     if (L.hitIdx < 0) {
       const float4_ medA = sc.matA[L.medium];
       L.result = vmul(L.rayI, mk(medA.x, medA.y, medA.z));   /* raytracer.h:544 */
-      return unwind(L, stack, cam);
+      act = ACT_UNWIND;
+    } else if (!significant(L.rayI)) {
+      act = ACT_UNWIND;                                      /* result left stale */
+    } else {
+      /* raytracer.h:171-181 for the winning sphere */
+      const V3 o = query_origin(L.qy);
+      const V3 d = mk(L.qy.dx, L.qy.dy, L.qy.dz);
+      const float4_ g = sc.geo[L.hitIdx];
+      L.obj = L.hitIdx;
+      L.P = vadd(o, vscale(L.minT, d));
+      L.Nrm = vunit(vsub(L.P, mk(g.x, g.y, g.z)));
+      const float opacity = sc.matA[L.obj].w;
+      if (opacity > 0.f) {
+        L.lit = mk(0.f, 0.f, 0.f);
+        L.light = 0;
+        act = (sc.nl > 0) ? ACT_SHADOW : ACT_MATTE;
+      } else {
+        act = ACT_NOMATTE;
+      }
     }
-    if (!significant(L.rayI)) return unwind(L, stack, cam);  /* result left stale */
-    /* raytracer.h:171-181 for the winning sphere */
-    const V3 o = query_origin(L.qy);
-    const V3 d = mk(L.qy.dx, L.qy.dy, L.qy.dz);
-    const float4_ g = sc.geo[L.hitIdx];
-    L.obj = L.hitIdx;
-    L.P = vadd(o, vscale(L.minT, d));
-    L.Nrm = vunit(vsub(L.P, mk(g.x, g.y, g.z)));
-    const float opacity = sc.matA[L.obj].w;
-    if (opacity > 0.f) {
-      L.lit = mk(0.f, 0.f, 0.f);
-      L.light = 0;
-      if (sc.nl > 0) { setup_shadow(L, sc); return false; }
-      return after_matte(L, sc, stack, cam, true);
-    }
-    return after_matte(L, sc, stack, cam, false);
-  }
-  if (L.kind == K_SHADOW) {
+  } else if (L.kind == K_SHADOW) {
     L.ctr.rays++; L.ctr.shadow++;
     const V3 d = mk(L.qy.dx, L.qy.dy, L.qy.dz);
     bool blocked = false;
@@ -515,30 +534,40 @@ RT_HD bool advance(Lane& L, const SceneView& sc, Frame* stack, const Camera& cam
         L.lit = vadd(L.lit, vscale(k, mk(lc.x, lc.y, lc.z)));
       }
     }
-    if (++L.light < (int)sc.nl) { setup_shadow(L, sc); return false; }
-    return after_matte(L, sc, stack, cam, true);
-  }
-  if (L.kind == K_CONTAIN) {
+    act = (++L.light < (int)sc.nl) ? ACT_SHADOW : ACT_MATTE;
+  } else if (L.kind == K_CONTAIN) {
     /* reference loop iterations (early return at the first container) */
     L.ctr.containT += (L.hitIdx >= 0) ? (uint32_t)(L.hitIdx + 1) : sc.n;
-    return after_contain(L, sc, stack, cam);
+    act = after_contain(L, sc, stack, cam);
+  } else {
+    return false;
   }
+  if (act >= ACT_MATTE) act = after_matte(L, sc, act == ACT_MATTE);
+  if (act == ACT_SHADOW) { setup_shadow(L, sc); return false; }
+  if (act == ACT_UNWIND) return unwind(L, stack, cam);
   return false;
 }
 
-/* Exact test of candidate sphere i for the lane's current query. */
-RT_HD void resolve_candidate(Lane& L, const SceneView& sc, uint32_t i) {
-  if (i >= sc.n) return;
-  const float4_ g = sc.geo[i];
-  L.ctr.exactTests++;
-  if (L.kind == K_CONTAIN) {
-    if (L.hitIdx < 0 && contains_exact(g, query_origin(L.qy))) L.hitIdx = (int)i;
+/* Exact test of candidate sphere i for a query of the given kind; updates the running
+ * closest hit (ray kinds) or first container (containment probe). */
+struct HitAcc { float minT; int hitIdx; };
+RT_HD HitAcc resolve_one(HitAcc h, int kind, V3 o, V3 d, float4_ g, uint32_t i) {
+  if (kind == K_CONTAIN) {
+    if (h.hitIdx < 0 && contains_exact(g, o)) h.hitIdx = (int)i;
   } else {
     float t;
-    if (ray_sphere_exact(g, query_origin(L.qy), mk(L.qy.dx, L.qy.dy, L.qy.dz), t)) {
-      if (t < L.minT) { L.minT = t; L.hitIdx = (int)i; }   /* strict: first index wins ties */
+    if (ray_sphere_exact(g, o, d, t)) {
+      if (t < h.minT) { h.minT = t; h.hitIdx = (int)i; }   /* strict: first index wins ties */
     }
   }
+  return h;
+}
+RT_HD void resolve_candidate(Lane& L, const SceneView& sc, uint32_t i) {
+  if (i >= sc.n) return;
+  L.ctr.exactTests++;
+  HitAcc h; h.minT = L.minT; h.hitIdx = L.hitIdx;
+  h = resolve_one(h, L.kind, query_origin(L.qy), mk(L.qy.dx, L.qy.dy, L.qy.dz), sc.geo[i], i);
+  L.minT = h.minT; L.hitIdx = h.hitIdx;
 }
 
 }  // namespace rtg

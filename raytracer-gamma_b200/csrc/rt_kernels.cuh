@@ -98,7 +98,20 @@ __device__ __forceinline__ bool work_to_pixel(const TraceParams& p, uint32_t idx
   return true;
 }
 
-template <bool USE_CONST, int MIN_BLOCKS>
+/* List overflow (more than RT_LIST_MAX candidates for one query): resolve what is queued.
+ * Rare and divergent, so it is kept out of line (and by value, so the lane state stays in
+ * registers) to keep the filter loop small. */
+__device__ __noinline__ HitAcc flush_list(HitAcc h, int kind, V3 o, V3 d, const float4_* geo,
+                                          uint32_t n, const unsigned short* sList, uint32_t tid) {
+#pragma unroll 1
+  for (int k = 0; k < RT_LIST_MAX; ++k) {
+    const uint32_t i = sList[k * RT_BLOCK + tid];
+    if (i < n) h = resolve_one(h, kind, o, d, geo[i], i);
+  }
+  return h;
+}
+
+template <bool USE_CONST, int MIN_BLOCKS, int GROUP>
 __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const TraceParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists] */
@@ -144,7 +157,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
   uint32_t wbase = 0, wend = 0;   /* warp-uniform slice of the tile queue */
   bool queueDry = false;
 
-  const uint32_t groups = p.sc.nPad >> 5;
+  const uint32_t groups = p.sc.nPad / GROUP;   /* nPad is a multiple of 32 */
 
   for (;;) {
     /* ---- refill ---- */
@@ -183,42 +196,54 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
     int cnt = 0;
     laneIters++;
     if (L.kind != K_NULL) activeIters++;
+    const bool filterable = query_filterable(L.qy);
     if (!p.noFilter) {
       for (uint32_t g = 0; g < groups; ++g) {
-        unsigned mask = 0;
+        /* bit (GROUP-1-j) of `skip` = sign bit of test j: one FADD + one funnel shift per test */
+        unsigned skip = 0;
 #pragma unroll
-        for (int j = 0; j < 32; ++j) {
+        for (int j = 0; j < GROUP; ++j) {
           float4 s4;
           if (USE_CONST) {
-            const float4_ c = c_filt[g * 32 + j];
+            const float4_ c = c_filt[g * GROUP + j];
             s4 = make_float4(c.x, c.y, c.z, c.w);
           } else {
-            s4 = sFilt[g * 32 + j];
+            s4 = sFilt[g * GROUP + j];
           }
           float4_ s; s.x = s4.x; s.y = s4.y; s.z = s4.z; s.w = s4.w;
-          if (filter_pass(L.qy, s)) mask |= (1u << j);
+          skip = __funnelshift_l(__float_as_uint(filter_diff(L.qy, s)), skip, 1);
         }
-        if (mask) {
+        unsigned cand = ~skip & (GROUP == 32 ? 0xFFFFFFFFu : ((1u << (GROUP & 31)) - 1u));
+        if (cand) {
           do {
-            const int j = __ffs(mask) - 1;
-            mask &= mask - 1;
+            const int b = 31 - __clz(cand);          /* highest bit = lowest sphere index */
+            cand &= ~(1u << b);
             if (cnt == RT_LIST_MAX) {
-              /* list full: resolve what we have now (rare, divergent) */
-#pragma unroll 1
-              for (int k = 0; k < RT_LIST_MAX; ++k)
-                resolve_candidate(L, p.sc, sList[k * RT_BLOCK + tid]);
+              HitAcc h; h.minT = L.minT; h.hitIdx = L.hitIdx;
+              h = flush_list(h, L.kind, query_origin(L.qy), mk(L.qy.dx, L.qy.dy, L.qy.dz), p.sc.geo,
+                             p.sc.n, sList, tid);
+              L.minT = h.minT; L.hitIdx = h.hitIdx;
+              L.ctr.exactTests += RT_LIST_MAX;
               cnt = 0;
             }
-            sList[cnt * RT_BLOCK + tid] = (unsigned short)(g * 32 + j);
+            sList[cnt * RT_BLOCK + tid] = (unsigned short)(g * GROUP + (GROUP - 1 - b));
             ++cnt;
-          } while (mask);
+          } while (cand);
         }
       }
       /* ---- resolve (convergent over lanes) ---- */
-      const int maxc = __reduce_max_sync(FULL, cnt);
+      if (filterable) {
+        const int maxc = __reduce_max_sync(FULL, cnt);
 #pragma unroll 1
-      for (int k = 0; k < maxc; ++k) {
-        if (k < cnt) resolve_candidate(L, p.sc, sList[k * RT_BLOCK + tid]);
+        for (int k = 0; k < maxc; ++k) {
+          if (k < cnt) resolve_candidate(L, p.sc, sList[k * RT_BLOCK + tid]);
+        }
+      } else {
+        /* not reached by any finite scene; keeps NaN/inf geometry on the reference's own path */
+        (void)__reduce_max_sync(FULL, 0);
+        L.minT = 1000.f; L.hitIdx = -1;
+        if (L.kind != K_NULL)
+          for (uint32_t i = 0; i < p.sc.n; ++i) resolve_candidate(L, p.sc, i);
       }
     } else {
       if (L.kind != K_NULL && L.qy.q != INFINITY)

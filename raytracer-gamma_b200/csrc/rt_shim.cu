@@ -16,6 +16,7 @@
 using namespace rtg;
 
 #define RT_DEFAULT_MIN_BLOCKS 2
+#define RT_DEFAULT_GROUP 32
 
 struct rt_cuda_ctx {
   int device = 0;
@@ -44,7 +45,7 @@ struct rt_cuda_ctx {
   void* hPinned = nullptr; size_t pinnedCap = 0;
 
   /* options */
-  int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0;
+  int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0, group = 0;
 
   /* stats */
   rt_cuda_stats stats{};
@@ -162,6 +163,7 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!ctx || !key) return RT_CUDA_ERR_INVALID_ARG;
   if (!strcmp(key, "staging")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->staging = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
+  if (!strcmp(key, "group")) { if (value != 0 && value != 8 && value != 16 && value != 32) return RT_CUDA_ERR_INVALID_ARG; ctx->group = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "min_blocks")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->minBlocks = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
   return RT_CUDA_ERR_INVALID_ARG;
@@ -259,8 +261,11 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   /* register budget variant: MIN_BLOCKS resident CTAs per SM (2: 128 regs, 3: 80, 4: 64) */
   int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
   void (*kern)(const TraceParams) = nullptr;
-  if (useConst) kern = (minBlocks == 2) ? trace_kernel<true, 2> : (minBlocks == 3) ? trace_kernel<true, 3> : trace_kernel<true, 4>;
-  else          kern = (minBlocks == 2) ? trace_kernel<false, 2> : (minBlocks == 3) ? trace_kernel<false, 3> : trace_kernel<false, 4>;
+  const int group = ctx->group ? ctx->group : RT_DEFAULT_GROUP;
+#define RT_PICK(C, M) ((group == 8) ? trace_kernel<C, M, 8> : (group == 16) ? trace_kernel<C, M, 16> : trace_kernel<C, M, 32>)
+  if (useConst) kern = (minBlocks == 2) ? RT_PICK(true, 2) : (minBlocks == 3) ? RT_PICK(true, 3) : RT_PICK(true, 4);
+  else          kern = (minBlocks == 2) ? RT_PICK(false, 2) : (minBlocks == 3) ? RT_PICK(false, 3) : RT_PICK(false, 4);
+#undef RT_PICK
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSM = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, RT_BLOCK, smem));

@@ -11,12 +11,13 @@ print("ffma_peak TFLOP/s:", [round(r.ffma_peak(8192), 2) for _ in range(3)])
 cases = [
     ("default 1080p a1 s4", pkg.default_scene(), 1920, 1080, 1.0, 4, {}),
     ("synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {}),
-    ("synth256 4K a1 s6 const", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"staging": 1}),
-    ("synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {}),
-    ("synth1024 4K a1 s8 mb3", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3}),
-    ("synth1024 4K a1 s8 mb4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4}),
+    ("synth256 4K a1 s6 g16", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"group": 16}),
     ("synth256 4K a1 s6 mb3", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 3}),
-    ("synth256 4K a1 s6 mb4", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 4}),
+    ("synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {}),
+    ("synth1024 4K a1 s8 g16", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"group": 16}),
+    ("synth1024 4K a1 s8 g8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"group": 8}),
+    ("synth1024 4K a1 s8 mb3", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3}),
+    ("synth1024 4K a1 s8 mb3 g16", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "group": 16}),
     ("synth16 4K a1 s8", pkg.synth_scene(16, 4), 3840, 2160, 1.0, 8, {}),
     ("synth4096 2K a1 s8", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {}),
 ]
