@@ -59,8 +59,10 @@ typedef struct rt_cuda_stats {
   uint64_t contain_tests;   /* its loop iterations, counted as the reference executes them          */
   uint64_t exact_tests;     /* candidates that went through the exact expressions                   */
   uint64_t samples;         /* rayTrace calls (main.cpp:439)                                        */
-  uint64_t lane_iters;      /* sphere-loop passes x 32 lanes                                        */
-  uint64_t active_lane_iters; /* of which lanes that carried a query                                */
+  uint64_t lane_iters;      /* sub-query capacity of all sphere passes (lanes x sub-queries per lane)      */
+  uint64_t active_lane_iters; /* sub-queries actually served                                       */
+  uint64_t served_trace, served_shadow, served_contain;   /* ... by kind                           */
+  uint64_t passes;          /* warp-level passes over the sphere list                               */
   uint64_t filter_tests;    /* discriminant filter tests executed = lane_iters * padded sphere count */
   uint64_t null_rays;       /* rays with direction 0 (total internal reflection): certain miss, no sphere loop */
   uint32_t sph_num, sph_padded, lgt_num;
@@ -117,7 +119,8 @@ int rt_cuda_synchronize(rt_cuda_ctx* ctx);
 
 /* Tuning / debug switches: "staging" 0 auto | 1 __constant__ | 2 shared (TMA bulk);
  * "no_filter" 1 = exact test against every sphere; "blocks_per_sm" 0 auto;
- * "min_blocks" 0 auto | 2 | 3 | 4 = register-budget variant of the trace kernel. */
+ * "min_blocks" 0 auto | 2 | 3 = register-budget variant of the trace kernel;
+ * "slots" 0 auto | 2 | 3 | 4 = pixels in flight per lane. */
 int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value);
 
 int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out);

@@ -73,6 +73,8 @@ class Stats(ctypes.Structure):
         ("contain_queries", ctypes.c_uint64), ("contain_tests", ctypes.c_uint64),
         ("exact_tests", ctypes.c_uint64), ("samples", ctypes.c_uint64),
         ("lane_iters", ctypes.c_uint64), ("active_lane_iters", ctypes.c_uint64),
+        ("served_trace", ctypes.c_uint64), ("served_shadow", ctypes.c_uint64),
+        ("served_contain", ctypes.c_uint64), ("passes", ctypes.c_uint64),
         ("filter_tests", ctypes.c_uint64), ("null_rays", ctypes.c_uint64),
         ("sph_num", ctypes.c_uint32), ("sph_padded", ctypes.c_uint32), ("lgt_num", ctypes.c_uint32),
         ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("local_rows", ctypes.c_uint32),

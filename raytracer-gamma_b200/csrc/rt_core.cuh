@@ -1,29 +1,30 @@
-/* rt_core.cuh — the per-lane trace machine of the B200 trace loop.
+/* rt_core.cuh — the trace machine of the B200 trace loop (host/device portable).
  *
  * What it computes is the reference's CPU copy of the algorithm
  * (/root/reference/raytracer_gamma/raytracer.h:81-842, pixel loop
  * main.cpp:383-453); how it computes it is new:
  *
  *  - The reference recurses through an explicit stack of 168-byte snapshots
- *    (raytraceStack.h:13-68).  Here every lane runs a small state machine whose
- *    only convergence point is "run one QUERY against all N spheres".  A query
- *    is a trace ray (closest hit, raytracer.h:145), a shadow ray
- *    (raytracer.h:272) or a point-containment probe (raytracer.h:245); all three
- *    use the same fused-multiply-add sphere loop (rt_kernels.cu), so a warp
- *    stays converged through the O(N) work no matter what its lanes are doing.
+ *    (raytraceStack.h:13-68).  Here a pixel in flight is a SLOT: a small state
+ *    record whose only suspension point is "one QUERY against all N spheres".
+ *    A query is a trace ray (closest hit, raytracer.h:145), a BATCH of up to four
+ *    shadow rays that share their origin (one per light, raytracer.h:272,328) or
+ *    a point-containment probe (raytracer.h:245).  The kernel (rt_kernels.cuh)
+ *    keeps several slots per lane and, every pass, lets the warp vote for the
+ *    query kind most of its lanes can serve, so each pass over the spheres runs a
+ *    loop specialised for ONE kind with all lanes converged.
  *  - A suspended call keeps 14 words (colour, the pre-computed reflected ray and
  *    its intensity, the medium) instead of a 168-byte snapshot.
  *  - Every value that can change a discrete decision or is carried into the
  *    image is evaluated with single IEEE-754 binary32 operations in the
- *    reference's expression order (the ex_* helpers below: __fmul_rn/__fadd_rn/
+ *    reference's expression order (the ex_* helpers: __fmul_rn/__fadd_rn/
  *    __fdiv_rn/__fsqrt_rn never contract into FMAs), so the float framebuffer is
  *    bit-identical to the reference CPU render.  The FMA filter only decides
- *    which spheres CANNOT be hit; see Filter below for the bound.
+ *    which spheres CANNOT be hit; see "Filter" below for the bound.
  *
  * The file is host/device portable on purpose: tests/hostsim.cpp runs the same
- * machine lane-by-lane on the CPU to check the state machine against the
- * oracle without a GPU.  That build is test infrastructure; the product path
- * is the CUDA kernel only.
+ * machine slot by slot on the CPU to check it against the oracle without a GPU.
+ * That build is test infrastructure; the product path is the CUDA kernel only.
  */
 #ifndef RT_CORE_CUH
 #define RT_CORE_CUH
@@ -33,8 +34,13 @@
 
 #if defined(__CUDACC__)
 #define RT_HD __host__ __device__ __forceinline__
+/* out-of-line on the device: IEEE division / square root expand to ~15 instructions plus a
+ * slow path each, and the O(1) shading code uses them ~50 times; one copy keeps the kernel's
+ * instruction footprint (and with it the instruction-cache miss rate) small */
+#define RT_HD_NI __host__ __device__ __noinline__
 #else
 #define RT_HD static inline
+#define RT_HD_NI static
 #endif
 
 namespace rtg {
@@ -44,13 +50,13 @@ namespace rtg {
 RT_HD float ex_add(float a, float b) { return __fadd_rn(a, b); }
 RT_HD float ex_sub(float a, float b) { return __fadd_rn(a, -b); }
 RT_HD float ex_mul(float a, float b) { return __fmul_rn(a, b); }
-RT_HD float ex_div(float a, float b) { return __fdiv_rn(a, b); }
-RT_HD float ex_sqrt(float a) { return __fsqrt_rn(a); }
+RT_HD_NI float ex_div(float a, float b) { return __fdiv_rn(a, b); }
+RT_HD_NI float ex_sqrt(float a) { return __fsqrt_rn(a); }
 RT_HD double exd_add(double a, double b) { return __dadd_rn(a, b); }
 RT_HD double exd_sub(double a, double b) { return __dadd_rn(a, -b); }
 RT_HD double exd_mul(double a, double b) { return __dmul_rn(a, b); }
-RT_HD double exd_div(double a, double b) { return __ddiv_rn(a, b); }
-RT_HD double exd_sqrt(double a) { return __dsqrt_rn(a); }
+RT_HD_NI double exd_div(double a, double b) { return __ddiv_rn(a, b); }
+RT_HD_NI double exd_sqrt(double a) { return __dsqrt_rn(a); }
 RT_HD float fast_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 #else
 /* host build: compiled with -ffp-contract=off, so these stay separate operations */
@@ -99,9 +105,9 @@ struct SceneView {
  * reference's float radicand (raytracer.h:95-105) approximates
  *     D = 4 [ (d.delta)^2 - A (|delta|^2 - r^2) ],   delta = o - c.
  * The filter evaluates, with FMAs and d pre-scaled to unit length,
- *     lhs = (d'.(o-c))^2 - q            q  = |o|^2 (1-kappa)
+ *     lhs = (d'.(o-c))^2 - q            q  = |o|^2 (1-kappa)   (stored negated: nq)
  *     ch  = w - 2 o.c                    w  = |c|^2 - r^2 - kappa(|c|^2+r^2) - 2.5e-6 r - 1e-11
- * and declares a CERTAIN MISS iff lhs < ch, i.e. iff
+ * and declares a CERTAIN MISS iff lhs - ch < 0, i.e. iff
  *     (d'.delta)^2 < |delta|^2 - r^2 - kappa(|o|^2+|c|^2+r^2) - (container slack).
  * kappa = 2^-17 = 128 u covers (first-order, u = 2^-24): 17u A(|delta|^2+r^2)
  * rounding of the reference's own non-fused radicand, 4u for its rounded delta,
@@ -109,81 +115,66 @@ struct SceneView {
  * for ch, 8u|delta|^2 for the unit scaling — about 92u(|o|^2+|c|^2)+31u r^2 in
  * total, using |delta|^2 <= 2(|o|^2+|c|^2).  Anything not a certain miss goes
  * through the reference's exact expressions, so a loose bound costs time, never
- * correctness; a NaN anywhere compares false and is therefore kept.
- * With d' = 0 the same records answer the containment probe of
- * raytracer.h:245-270: lhs < ch  <=>  |p-c|^2 > r^2 + slack, and the slack
+ * correctness.  The ch part depends on the origin only: the shadow rays of one hit
+ * share it.  With no direction (lhs = -q) the same records answer the containment
+ * probe of raytracer.h:245-270: -q - ch < 0 <=> |p-c|^2 > r^2 + slack, and the slack
  * exceeds (r+1e-6)^2 - r^2.
+ * lhs and ch are finite (or ch = +inf for padding records), and the rounded
+ * difference of two such values carries the sign of the exact difference, so the
+ * kernel just collects SIGN BITS.  Geometry that is not finite never reaches the
+ * filter (origin_filterable / dir_filterable): it is tested exactly against every
+ * sphere instead.
  */
 #define RT_KAPPA 7.62939453125e-06f   /* 2^-17 */
 
-struct Query {
-  float ndx, ndy, ndz, od;   /* -d', d'.o  (d' = d/|d|)                       */
-  float px, py, pz, q;       /* -2o, |o|^2(1-kappa); q=+inf never flags       */
-  float dx, dy, dz;          /* exact direction for the ray kinds             */
-};
+struct OriginQ { float px, py, pz, nq; };    /* -2o, -|o|^2(1-kappa) (never -0) */
+struct DirQ { float ndx, ndy, ndz, od; };    /* -d', d'.o   (d' = d/|d|)       */
 
-enum { K_NULL = 0, K_TRACE = 1, K_SHADOW = 2, K_CONTAIN = 3 };
-
-RT_HD void query_null(Query& qy) {
-  qy.ndx = qy.ndy = qy.ndz = 0.f; qy.od = 0.f;
-  qy.px = qy.py = qy.pz = 0.f; qy.q = INFINITY;
-  qy.dx = qy.dy = qy.dz = 0.f;
+RT_HD OriginQ make_origin(V3 o) {
+  OriginQ O;
+  O.px = -2.f * o.x; O.py = -2.f * o.y; O.pz = -2.f * o.z;
+  const float oo = fast_fma(o.z, o.z, fast_fma(o.y, o.y, ex_mul(o.x, o.x)));
+  O.nq = ex_sub(0.f, ex_mul(oo, 1.f - RT_KAPPA));   /* 0 - q: +0 when q is 0, so no test value is ever -0 */
+  return O;
 }
 
-/* Ray query.  Returns false when d == 0: the reference then computes
- * a = b = 0, radicand = 0, u = 0/0 = NaN for every sphere (raytracer.h:98-116),
- * i.e. a guaranteed miss, so the sphere loop is skipped for that lane. */
-RT_HD bool query_ray(Query& qy, V3 o, V3 d) {
+/* Direction part of a ray query.  Returns false when d == 0: the reference then
+ * computes a = b = 0, radicand = 0, u = 0/0 = NaN for every sphere
+ * (raytracer.h:98-116), i.e. a guaranteed miss — such a ray needs no sphere loop. */
+RT_HD bool make_dir(DirQ& D, V3 o, V3 d) {
   const float A = vdot(d, d);
-  qy.dx = d.x; qy.dy = d.y; qy.dz = d.z;
-  qy.px = -2.f * o.x; qy.py = -2.f * o.y; qy.pz = -2.f * o.z;
   if (!(A > 0.f) && !(A != A)) {   /* A == 0 (not NaN) */
-    qy.ndx = qy.ndy = qy.ndz = 0.f; qy.od = 0.f; qy.q = INFINITY;
+    D.ndx = D.ndy = D.ndz = 0.f; D.od = 0.f;
     return false;
   }
   const float s = ex_div(1.f, ex_sqrt(A));
   const float ux = ex_mul(d.x, s), uy = ex_mul(d.y, s), uz = ex_mul(d.z, s);
-  qy.ndx = -ux; qy.ndy = -uy; qy.ndz = -uz;
-  qy.od = fast_fma(uz, o.z, fast_fma(uy, o.y, ex_mul(ux, o.x)));
-  const float oo = fast_fma(o.z, o.z, fast_fma(o.y, o.y, ex_mul(o.x, o.x)));
-  qy.q = ex_mul(oo, 1.f - RT_KAPPA);
+  D.ndx = -ux; D.ndy = -uy; D.ndz = -uz;
+  D.od = fast_fma(uz, o.z, fast_fma(uy, o.y, ex_mul(ux, o.x)));
   return true;
 }
 
-RT_HD void query_point(Query& qy, V3 p) {
-  qy.ndx = qy.ndy = qy.ndz = 0.f; qy.od = 0.f;
-  qy.dx = qy.dy = qy.dz = 0.f;
-  qy.px = -2.f * p.x; qy.py = -2.f * p.y; qy.pz = -2.f * p.z;
-  const float oo = fast_fma(p.z, p.z, fast_fma(p.y, p.y, ex_mul(p.x, p.x)));
-  qy.q = ex_mul(oo, 1.f - RT_KAPPA);
+RT_HD float filter_ch(const OriginQ& O, float4_ s) {
+  float ch = fast_fma(O.px, s.x, s.w);
+  ch = fast_fma(O.py, s.y, ch);
+  return fast_fma(O.pz, s.z, ch);
 }
-
-RT_HD V3 query_origin(const Query& qy) { return mk(-0.5f * qy.px, -0.5f * qy.py, -0.5f * qy.pz); }
-
-/* One filter test.  Returns lhs - ch: NEGATIVE (sign bit set) means certain miss; zero
- * or positive means the sphere may be hit / may contain the point.  lhs and ch are finite
- * or -inf/+inf by construction (null queries, padding), and the rounded difference of two
- * such values carries the sign of the exact difference, so "sign bit set" <=> lhs < ch.
- * Queries with NaN/inf geometry never reach the filter (query_filterable). */
-RT_HD float filter_diff(const Query& qy, float4_ s) {
-  float bq = fast_fma(qy.ndx, s.x, qy.od);
-  bq = fast_fma(qy.ndy, s.y, bq);
-  bq = fast_fma(qy.ndz, s.z, bq);
-  float ch = fast_fma(qy.px, s.x, s.w);
-  ch = fast_fma(qy.py, s.y, ch);
-  ch = fast_fma(qy.pz, s.z, ch);
-  const float lhs = fast_fma(bq, bq, -qy.q);
-  return ex_sub(lhs, ch);
+/* Ray test: negative <=> certain miss. */
+RT_HD float filter_ray(const OriginQ& O, const DirQ& D, float ch, float4_ s) {
+  float bq = fast_fma(D.ndx, s.x, D.od);
+  bq = fast_fma(D.ndy, s.y, bq);
+  bq = fast_fma(D.ndz, s.z, bq);
+  return ex_sub(fast_fma(bq, bq, O.nq), ch);
 }
-RT_HD bool filter_pass(const Query& qy, float4_ s) { return !(filter_diff(qy, s) < 0.f); }
+/* Containment test: negative <=> certainly outside. */
+RT_HD float filter_point(const OriginQ& O, float ch) { return ex_sub(O.nq, ch); }
 
-/* The sign-bit form of the filter is only conservative for non-NaN inputs.  A query whose
- * numbers are not all finite (q = +inf marks a null query and is fine) skips the filter and
- * is tested exactly against every sphere. */
 RT_HD bool finite_f(float x) { return fabsf(x) <= 3.402823466e+38f; }
-RT_HD bool query_filterable(const Query& qy) {
-  return finite_f(qy.ndx) && finite_f(qy.ndy) && finite_f(qy.ndz) && finite_f(qy.od) &&
-         finite_f(qy.px) && finite_f(qy.py) && finite_f(qy.pz) && !(qy.q != qy.q) && qy.q > -INFINITY;
+RT_HD bool origin_filterable(const OriginQ& O) {
+  return finite_f(O.px) && finite_f(O.py) && finite_f(O.pz) && finite_f(O.nq);
+}
+RT_HD bool dir_filterable(const DirQ& D) {
+  return finite_f(D.ndx) && finite_f(D.ndy) && finite_f(D.ndz) && finite_f(D.od);
 }
 
 /* ---- exact per-candidate tests --------------------------------------------- */
@@ -193,22 +184,23 @@ RT_HD bool query_filterable(const Query& qy) {
  * answer (or, if u1 >= 10000, so is u0 and there is none) and u0 need not be
  * divided out; u0 is only formed when u1 fails the lower bound (or is NaN).
  * Same decisions, same t, one IEEE division less on the common path. */
-RT_HD bool ray_sphere_exact(float4_ g, V3 o, V3 d, float& t) {
+RT_HD_NI float ray_sphere_t(float4_ g, V3 o, V3 d) {   /* t of the hit, or -1 when there is none */
   const V3 disp = vsub(o, mk(g.x, g.y, g.z));
   const float a = vdot(d, d);
   const float b = ex_mul(2.0f, vdot(d, disp));
   const float c = ex_sub(vdot(disp, disp), ex_mul(g.w, g.w));
   const float radicand = ex_sub(ex_mul(b, b), ex_mul(ex_mul(4.0f, a), c));
-  if (!(radicand >= 0.0f)) return false;
+  if (!(radicand >= 0.0f)) return -1.f;
   const float root = ex_sqrt(radicand);
   const float denom = ex_mul(2.0f, a);
   const float u1 = ex_div(ex_sub(-b, root), denom);
-  if (u1 > 1.0e-5f) {
-    if (u1 < 10000.f) { t = u1; return true; }
-    return false;
-  }
+  if (u1 > 1.0e-5f) return (u1 < 10000.f) ? u1 : -1.f;
   const float u0 = ex_div(ex_add(-b, root), denom);
-  if (u0 > 1.0e-5f && u0 < 10000.f) { t = u0; return true; }
+  return (u0 > 1.0e-5f && u0 < 10000.f) ? u0 : -1.f;
+}
+RT_HD bool ray_sphere_exact(float4_ g, V3 o, V3 d, float& t) {
+  const float r = ray_sphere_t(g, o, d);
+  if (r > 0.f) { t = r; return true; }
   return false;
 }
 
@@ -221,6 +213,7 @@ RT_HD bool contains_exact(float4_ g, V3 p) {
 
 /* ---- suspended calls -------------------------------------------------------- */
 #define RT_MAX_STACK 16
+#define RT_SHADOW_BATCH 4
 struct Frame {            /* 16 words: one 64-byte local-memory record */
   V3 colour;              /* cur.colour at suspension                                  */
   float stage;            /* 1.f: waiting for the refracted child, 2.f: reflected child */
@@ -234,26 +227,32 @@ struct Counters {         /* per-lane tallies, reduced per block at the end */
   uint32_t nullRays;      /* rays with d == 0: answered without running the sphere loop */
 };
 
-/* ---- the lane ---------------------------------------------------------------- */
-struct Lane {
-  Query qy;
-  int kind;
-  /* result of the sphere loop */
-  float minT; int hitIdx;
-  /* the call being evaluated ("currSnapshot") */
-  V3 rayD, rayI, colour;
+enum { K_NULL = 0, K_TRACE = 1, K_SHADOW = 2, K_CONTAIN = 3 };
+
+/* ---- a pixel in flight --------------------------------------------------------- */
+struct Slot {
+  int kind;               /* the pending query */
+  uint32_t pixel;         /* destination index, 0xFFFFFFFF = free slot */
+  int si, sj;             /* sample being traced */
+  int top;                /* frames on the stack = depth of the current call */
   int medium;             /* sphere index of the medium the ray travels in, n = ambient */
   int obj;                /* struck sphere */
-  V3 P, Nrm;
-  /* matte accumulation */
-  int light; V3 lit; float gap;
-  /* "colourSum" of raytracer.h:425 */
-  V3 result;
-  int top;                /* frames on the stack = depth of the current call */
-  /* pixel / sample bookkeeping */
-  int si, sj; V3 acc; float pxw, pyw;
-  uint32_t pixel;         /* destination index, 0xFFFFFFFF = lane has no pixel */
-  Counters ctr;
+  int light;              /* first light of the current shadow batch */
+  int ndirs;              /* directions in the pending query (1 for a trace ray) */
+  float pxw, pyw;
+  V3 acc;                 /* pixel accumulator, main.cpp:420,446 */
+  V3 result;              /* "colourSum" of raytracer.h:425 */
+  V3 colour, rayD, rayI;  /* the call being evaluated ("currSnapshot") */
+  V3 P, Nrm;              /* its hit */
+  V3 lit;                 /* matte accumulation, raytracer.h:325 */
+  /* geometry of the pending query */
+  V3 qo;                  /* ray origin / probe point */
+  V3 qd[RT_SHADOW_BATCH]; /* direction(s): qd[0] for a trace ray, one per light for a shadow batch */
+  float gap[RT_SHADOW_BATCH];   /* squared distance to the light, raytracer.h:280 */
+  /* answer, filled by the sphere pass */
+  float minT; int hitIdx; /* closest hit (trace) / first container (probe) */
+  uint32_t blocked;       /* shadow batch: bit k = light `light+k` is occluded */
+  Frame stack[RT_MAX_STACK];
 };
 
 struct Camera {           /* main.cpp:384-402, evaluated once on the host in float */
@@ -279,83 +278,95 @@ RT_HD Camera make_camera(uint32_t W, uint32_t H, float zoom, float alias, int S,
   return c;
 }
 
-/* Start the sample (si, sj) of the lane's pixel: main.cpp:432-441 */
-RT_HD void start_sample(Lane& L, const Camera& cam) {
-  const float x = ex_mul(ex_add(L.pxw, ex_mul((float)L.sj, cam.aliasStep)), cam.aspect);
-  const float y = ex_add(L.pyw, ex_mul((float)L.si, cam.aliasStep));
-  const V3 d = vunit(mk(x, y, cam.zoom));
-  L.rayD = d; L.rayI = mk(1.f, 1.f, 1.f); L.colour = mk(0.f, 0.f, 0.f);
-  L.result = mk(0.f, 0.f, 0.f);
-  L.medium = cam.ambient;                  /* every sample starts in the ambient medium, main.cpp:439 */
-  L.top = -1;
-  L.ctr.samples++;
-  L.kind = K_TRACE;
-  L.minT = 1000.f; L.hitIdx = -1;
-  query_ray(L.qy, mk(0.f, 0.f, 0.f), d);   /* d is unit: never the null case */
+RT_HD void set_trace_query(Slot& s, Counters& ctr, V3 o, V3 d) {
+  s.kind = K_TRACE;
+  s.ndirs = 1;
+  s.qo = o; s.qd[0] = d;
+  s.minT = 1000.f; s.hitIdx = -1;
+  if (vdot(d, d) == 0.f) ctr.nullRays++;   /* zero direction: certain miss (see make_dir) */
 }
 
-/* Give the lane pixel (gx, gy) of the full frame, stored at dst index `pixel`. */
-RT_HD bool start_pixel(Lane& L, const Camera& cam, uint32_t gx, uint32_t gy, uint32_t pixel) {
-  L.pixel = pixel;
-  L.pxw = ex_mul(ex_sub((float)gx, ex_mul((float)cam.W, 0.5f)), cam.stepX);
-  L.pyw = ex_mul(ex_sub(ex_mul((float)cam.H, 0.5f), (float)gy), cam.stepY);
-  L.acc = mk(0.f, 0.f, 0.f);
-  L.si = 0; L.sj = 0;
-  if (cam.nIter <= 0) { L.kind = K_NULL; query_null(L.qy); return false; }
-  start_sample(L, cam);
+/* Start the sample (si, sj) of the slot's pixel: main.cpp:432-441 */
+RT_HD void start_sample(Slot& s, Counters& ctr, const Camera& cam) {
+  const float x = ex_mul(ex_add(s.pxw, ex_mul((float)s.sj, cam.aliasStep)), cam.aspect);
+  const float y = ex_add(s.pyw, ex_mul((float)s.si, cam.aliasStep));
+  const V3 d = vunit(mk(x, y, cam.zoom));
+  s.rayD = d; s.rayI = mk(1.f, 1.f, 1.f); s.colour = mk(0.f, 0.f, 0.f);
+  s.result = mk(0.f, 0.f, 0.f);
+  s.medium = cam.ambient;                  /* every sample starts in the ambient medium, main.cpp:439 */
+  s.top = -1;
+  ctr.samples++;
+  set_trace_query(s, ctr, mk(0.f, 0.f, 0.f), d);
+}
+
+/* Give the slot pixel (gx, gy) of the full frame, stored at dst index `pixel`.
+ * Returns false when the pixel needs no samples (alias <= 0: the pixel is black). */
+RT_HD bool start_pixel(Slot& s, Counters& ctr, const Camera& cam, uint32_t gx, uint32_t gy,
+                       uint32_t pixel) {
+  s.pixel = pixel;
+  s.pxw = ex_mul(ex_sub((float)gx, ex_mul((float)cam.W, 0.5f)), cam.stepX);
+  s.pyw = ex_mul(ex_sub(ex_mul((float)cam.H, 0.5f), (float)gy), cam.stepY);
+  s.acc = mk(0.f, 0.f, 0.f);
+  s.si = 0; s.sj = 0;
+  if (cam.nIter <= 0) { s.kind = K_NULL; return false; }
+  start_sample(s, ctr, cam);
   return true;
 }
 
-RT_HD void set_ray_query(Lane& L, int kind, V3 o, V3 d) {
-  L.kind = kind;
-  L.minT = 1000.f; L.hitIdx = -1;
-  if (!query_ray(L.qy, o, d)) L.ctr.nullRays++;
-}
-
-/* raytracer.h:272-286: shadow ray towards light `L.light` */
-RT_HD void setup_shadow(Lane& L, const SceneView& sc) {
-  const float4_ lp = sc.lpos[L.light];
-  const V3 dir = vsub(mk(lp.x, lp.y, lp.z), L.P);
-  L.gap = vdot(dir, dir);
-  set_ray_query(L, K_SHADOW, L.P, vunit(dir));
+/* raytracer.h:272-286 for the lights light .. light+ndirs-1: shadow rays from P */
+RT_HD void setup_shadow_batch(Slot& s, const SceneView& sc) {
+  int nb = (int)sc.nl - s.light;
+  if (nb > RT_SHADOW_BATCH) nb = RT_SHADOW_BATCH;
+  s.kind = K_SHADOW;
+  s.ndirs = nb;
+  s.qo = s.P;
+  s.blocked = 0u;
+  for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+    if (k < nb) {
+      const float4_ lp = sc.lpos[s.light + k];
+      const V3 dir = vsub(mk(lp.x, lp.y, lp.z), s.P);
+      s.gap[k] = vdot(dir, dir);
+      s.qd[k] = vunit(dir);
+    }
+  }
 }
 
 /* Sample finished: main.cpp:443-447.  Returns true when the pixel is complete. */
-RT_HD bool finish_sample(Lane& L, const Camera& cam) {
-  const V3 s = vscale(cam.inv, L.result);
-  L.acc = vadd(L.acc, s);
-  if (++L.sj >= cam.nIter) { L.sj = 0; ++L.si; }
-  if (L.si >= cam.nIter) return true;
-  start_sample(L, cam);
+RT_HD bool finish_sample(Slot& s, Counters& ctr, const Camera& cam) {
+  const V3 v = vscale(cam.inv, s.result);
+  s.acc = vadd(s.acc, v);
+  if (++s.sj >= cam.nIter) { s.sj = 0; ++s.si; }
+  if (s.si >= cam.nIter) return true;
+  start_sample(s, ctr, cam);
   return false;
 }
 
 /* Pop suspended calls until one launches a child ray or the stack is empty
  * (raytracer.h:552-628).  Returns true when the sample is finished. */
-RT_HD bool unwind(Lane& L, Frame* stack, const Camera& cam) {
-  while (L.top >= 0) {
-    Frame& f = stack[L.top];
-    --L.top;
-    L.colour = vadd(L.result, f.colour);
+RT_HD bool unwind(Slot& s, Counters& ctr, const Camera& cam) {
+  while (s.top >= 0) {
+    Frame& f = s.stack[s.top];
+    --s.top;
+    s.colour = vadd(s.result, f.colour);
     if (f.stage == 1.f) {
       if (significant(f.reflCol)) {
         /* re-push as stage 2 (always fits: the slot was just vacated) */
-        ++L.top;
-        f.colour = L.colour; f.stage = 2.f;
-        L.result = L.colour;
-        if (L.top < cam.S - 1) {
+        ++s.top;
+        f.colour = s.colour; f.stage = 2.f;
+        s.result = s.colour;
+        if (s.top < cam.S - 1) {
           /* reflected child, raytracer.h:602-611 */
-          L.rayD = f.reflD; L.rayI = f.reflCol; L.medium = (int)f.medium;
-          L.colour = mk(0.f, 0.f, 0.f);
-          set_ray_query(L, K_TRACE, f.reflO, f.reflD);
+          s.rayD = f.reflD; s.rayI = f.reflCol; s.medium = (int)f.medium;
+          s.colour = mk(0.f, 0.f, 0.f);
+          set_trace_query(s, ctr, f.reflO, f.reflD);
           return false;
         }
         /* child push dropped (raytraceStack.h:52): fall through to pop stage 2 */
         continue;
       }
-      L.result = L.colour;
+      s.result = s.colour;
     } else {
-      L.result = L.colour;
+      s.result = s.colour;
     }
   }
   return true;
@@ -375,22 +386,21 @@ RT_HD float fresnel_term(float n1, float n2, float cosA1, float cosA2) {
 }
 
 /* What a handler leaves for the common tail of advance(): each tail (shadow set-up,
- * matte/transparency step, unwinding) exists once, so lanes of different kinds
- * re-converge on it and the code stays small. */
+ * matte/transparency step, unwinding) exists once, so the code stays small. */
 enum { ACT_QUERY = 0, ACT_UNWIND = 1, ACT_SHADOW = 2, ACT_MATTE = 3, ACT_NOMATTE = 4 };
 
 /* After the containment probe: refraction (raytracer.h:642-815), suspend the
  * call (raytracer.h:516-522), launch the refracted child (raytracer.h:524-533). */
-RT_HD int after_contain(Lane& L, const SceneView& sc, Frame* stack, const Camera& cam) {
-  const int target = (L.hitIdx >= 0) ? L.hitIdx : (int)sc.n;
-  const float4_ objA = sc.matA[L.obj], objB = sc.matB[L.obj];
-  const float4_ medA = sc.matA[L.medium], medB = sc.matB[L.medium];
+RT_HD int after_contain(Slot& s, Counters& ctr, const SceneView& sc, const Camera& cam) {
+  const int target = (s.hitIdx >= 0) ? s.hitIdx : (int)sc.n;
+  const float4_ objA = sc.matA[s.obj], objB = sc.matB[s.obj];
+  const float4_ medA = sc.matA[s.medium], medB = sc.matB[s.medium];
   const float4_ tgtB = sc.matB[target];
   const float opacity = objA.w;
   const float transparency = ex_sub(1.f, opacity);
-  const V3 incI = vscale(transparency, L.rayI);          /* raytracer.h:498 */
+  const V3 incI = vscale(transparency, s.rayI);          /* raytracer.h:498 */
 
-  float cosA1 = vdot(L.rayD, L.Nrm);
+  float cosA1 = vdot(s.rayD, s.Nrm);
   float sinA1 = 0.f;
   if (cosA1 <= -1.0f) { cosA1 = -1.f; }
   else if (cosA1 >= 1.f) { cosA1 = 1.f; }
@@ -416,13 +426,13 @@ RT_HD int after_contain(Lane& L, const SceneView& sc, Frame* stack, const Camera
   float bestAlign = (float)-0.1;
   V3 rdir = mk(0.f, 0.f, 0.f);
   {
-    const V3 cand = vadd(L.rayD, vscale(r0, L.Nrm));
-    const float align = vdot(L.rayD, cand);
+    const V3 cand = vadd(s.rayD, vscale(r0, s.Nrm));
+    const float align = vdot(s.rayD, cand);
     if (align > bestAlign) { bestAlign = align; rdir = cand; }
   }
   if (nsol == 2) {
-    const V3 cand = vadd(L.rayD, vscale(r1, L.Nrm));
-    const float align = vdot(L.rayD, cand);
+    const V3 cand = vadd(s.rayD, vscale(r1, s.Nrm));
+    const float align = vdot(s.rayD, cand);
     if (align > bestAlign) { bestAlign = align; rdir = cand; }
   }
 
@@ -437,137 +447,136 @@ RT_HD int after_contain(Lane& L, const SceneView& sc, Frame* stack, const Camera
   const float prod = ex_mul(transparency, R);
   V3 rc = vscale(prod, mk(1.f, 1.f, 1.f));
   rc = vadd(rc, vscale(medA.w, mk(objB.x, objB.y, objB.z)));
-  rc = vmul(L.rayI, rc);
+  rc = vmul(s.rayI, rc);
 
   /* suspend (always fits: depth <= S-1) */
-  ++L.top;
-  Frame& f = stack[L.top];
-  f.colour = L.colour; f.stage = 1.f;
-  f.reflCol = rc; f.medium = (float)L.medium;
+  ++s.top;
+  Frame& f = s.stack[s.top];
+  f.colour = s.colour; f.stage = 1.f;
+  f.reflCol = rc; f.medium = (float)s.medium;
   if (significant(rc)) {
     /* raytracer.h:817-842 */
-    const float perp = ex_mul(2.f, vdot(L.rayD, L.Nrm));
-    const V3 rd = vunit(vsub(L.rayD, vscale(perp, L.Nrm)));
+    const float perp = ex_mul(2.f, vdot(s.rayD, s.Nrm));
+    const V3 rd = vunit(vsub(s.rayD, vscale(perp, s.Nrm)));
     f.reflD = rd;
-    f.reflO = vadd(L.P, vscale(0.01f, rd));
+    f.reflO = vadd(s.P, vscale(0.01f, rd));
   } else {
     f.reflD = mk(0.f, 0.f, 0.f); f.reflO = mk(0.f, 0.f, 0.f);
   }
-  L.result = L.colour;                                   /* raytracer.h:538 */
-  if (L.top < cam.S - 1) {
-    L.rayD = rdir; L.rayI = rint; L.medium = target;
-    L.colour = mk(0.f, 0.f, 0.f);
-    set_ray_query(L, K_TRACE, L.P, rdir);
+  s.result = s.colour;                                   /* raytracer.h:538 */
+  if (s.top < cam.S - 1) {
+    s.rayD = rdir; s.rayI = rint; s.medium = target;
+    s.colour = mk(0.f, 0.f, 0.f);
+    set_trace_query(s, ctr, s.P, rdir);
     return ACT_QUERY;
   }
   return ACT_UNWIND;                                     /* child push dropped */
 }
 
 /* Matte term complete (raytracer.h:468-484), then transparency (raytracer.h:494). */
-RT_HD int after_matte(Lane& L, const SceneView& sc, bool haveMatte) {
-  const float4_ objA = sc.matA[L.obj];
+RT_HD int after_matte(Slot& s, Counters& ctr, const SceneView& sc, bool haveMatte) {
+  const float4_ objA = sc.matA[s.obj];
   const float opacity = objA.w;
   if (haveMatte) {
-    V3 w = vmul(L.rayI, mk(objA.x, objA.y, objA.z));
+    V3 w = vmul(s.rayI, mk(objA.x, objA.y, objA.z));
     w = vscale(opacity, w);
-    w = vmul(L.lit, w);
-    L.colour = vadd(w, L.colour);
+    w = vmul(s.lit, w);
+    s.colour = vadd(w, s.colour);
   }
   const float transparency = ex_sub(1.f, opacity);
   if (transparency > 0.f) {
-    const V3 probe = vadd(vscale(0.01f, L.rayD), L.P);   /* raytracer.h:688-692 */
-    L.kind = K_CONTAIN;
-    L.hitIdx = -1; L.minT = 1000.f;
-    query_point(L.qy, probe);
-    L.ctr.containQ++;
+    s.kind = K_CONTAIN;
+    s.ndirs = 0;
+    s.qo = vadd(vscale(0.01f, s.rayD), s.P);             /* raytracer.h:688-692 */
+    s.hitIdx = -1; s.minT = 1000.f;
+    ctr.containQ++;
     return ACT_QUERY;
   }
-  L.result = L.colour;
+  s.result = s.colour;
   return ACT_UNWIND;
 }
 
-/* Advance the lane after its query has been answered (L.hitIdx / L.minT).
- * Returns true when the lane's current SAMPLE is finished (L.result valid);
- * otherwise L.qy / L.kind hold the next query. */
-RT_HD bool advance(Lane& L, const SceneView& sc, Frame* stack, const Camera& cam) {
+/* Advance the slot after its query has been answered (hitIdx/minT or blocked).
+ * Returns true when the slot's current SAMPLE is finished (result valid);
+ * otherwise the slot holds its next query. */
+RT_HD bool advance(Slot& s, Counters& ctr, const SceneView& sc, const Camera& cam) {
   int act;
-  if (L.kind == K_TRACE) {
-    L.ctr.rays++;
-    if (L.hitIdx < 0) {
-      const float4_ medA = sc.matA[L.medium];
-      L.result = vmul(L.rayI, mk(medA.x, medA.y, medA.z));   /* raytracer.h:544 */
+  if (s.kind == K_TRACE) {
+    ctr.rays++;
+    if (s.hitIdx < 0) {
+      const float4_ medA = sc.matA[s.medium];
+      s.result = vmul(s.rayI, mk(medA.x, medA.y, medA.z));   /* raytracer.h:544 */
       act = ACT_UNWIND;
-    } else if (!significant(L.rayI)) {
+    } else if (!significant(s.rayI)) {
       act = ACT_UNWIND;                                      /* result left stale */
     } else {
       /* raytracer.h:171-181 for the winning sphere */
-      const V3 o = query_origin(L.qy);
-      const V3 d = mk(L.qy.dx, L.qy.dy, L.qy.dz);
-      const float4_ g = sc.geo[L.hitIdx];
-      L.obj = L.hitIdx;
-      L.P = vadd(o, vscale(L.minT, d));
-      L.Nrm = vunit(vsub(L.P, mk(g.x, g.y, g.z)));
-      const float opacity = sc.matA[L.obj].w;
+      const float4_ g = sc.geo[s.hitIdx];
+      s.obj = s.hitIdx;
+      s.P = vadd(s.qo, vscale(s.minT, s.qd[0]));
+      s.Nrm = vunit(vsub(s.P, mk(g.x, g.y, g.z)));
+      const float opacity = sc.matA[s.obj].w;
       if (opacity > 0.f) {
-        L.lit = mk(0.f, 0.f, 0.f);
-        L.light = 0;
+        s.lit = mk(0.f, 0.f, 0.f);
+        s.light = 0;
         act = (sc.nl > 0) ? ACT_SHADOW : ACT_MATTE;
       } else {
         act = ACT_NOMATTE;
       }
     }
-  } else if (L.kind == K_SHADOW) {
-    L.ctr.rays++; L.ctr.shadow++;
-    const V3 d = mk(L.qy.dx, L.qy.dy, L.qy.dz);
-    bool blocked = false;
-    if (L.hitIdx >= 0) {
-      const V3 dist = vscale(L.minT, d);
-      blocked = vdot(dist, dist) < L.gap;                  /* raytracer.h:299 */
-    }
-    if (!blocked) {
-      /* raytracer.h:337-361; `d` is the same normalised vector calculateMatte rebuilds */
-      const float4_ lp = sc.lpos[L.light], lc = sc.lcol[L.light];
-      const V3 dist = vsub(mk(lp.x, lp.y, lp.z), L.P);
-      const float incidence = vdot(L.Nrm, d);
-      if (incidence > 0.f) {
-        const float k = ex_div(incidence, vdot(dist, dist));
-        L.lit = vadd(L.lit, vscale(k, mk(lc.x, lc.y, lc.z)));
+  } else if (s.kind == K_SHADOW) {
+    /* raytracer.h:328-363 for the lights of this batch, in index order */
+    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+      if (k < s.ndirs) {
+        ctr.rays++; ctr.shadow++;
+        if (!((s.blocked >> k) & 1u)) {
+          const float4_ lp = sc.lpos[s.light + k], lc = sc.lcol[s.light + k];
+          const V3 dist = vsub(mk(lp.x, lp.y, lp.z), s.P);
+          const float incidence = vdot(s.Nrm, s.qd[k]);   /* qd[k] = the vector calculateMatte rebuilds */
+          if (incidence > 0.f) {
+            const float kk = ex_div(incidence, vdot(dist, dist));
+            s.lit = vadd(s.lit, vscale(kk, mk(lc.x, lc.y, lc.z)));
+          }
+        }
       }
     }
-    act = (++L.light < (int)sc.nl) ? ACT_SHADOW : ACT_MATTE;
-  } else if (L.kind == K_CONTAIN) {
+    s.light += s.ndirs;
+    act = (s.light < (int)sc.nl) ? ACT_SHADOW : ACT_MATTE;
+  } else if (s.kind == K_CONTAIN) {
     /* reference loop iterations (early return at the first container) */
-    L.ctr.containT += (L.hitIdx >= 0) ? (uint32_t)(L.hitIdx + 1) : sc.n;
-    act = after_contain(L, sc, stack, cam);
+    ctr.containT += (s.hitIdx >= 0) ? (uint32_t)(s.hitIdx + 1) : sc.n;
+    act = after_contain(s, ctr, sc, cam);
   } else {
     return false;
   }
-  if (act >= ACT_MATTE) act = after_matte(L, sc, act == ACT_MATTE);
-  if (act == ACT_SHADOW) { setup_shadow(L, sc); return false; }
-  if (act == ACT_UNWIND) return unwind(L, stack, cam);
+  if (act >= ACT_MATTE) act = after_matte(s, ctr, sc, act == ACT_MATTE);
+  if (act == ACT_SHADOW) { setup_shadow_batch(s, sc); return false; }
+  if (act == ACT_UNWIND) return unwind(s, ctr, cam);
   return false;
 }
 
-/* Exact test of candidate sphere i for a query of the given kind; updates the running
- * closest hit (ray kinds) or first container (containment probe). */
-struct HitAcc { float minT; int hitIdx; };
-RT_HD HitAcc resolve_one(HitAcc h, int kind, V3 o, V3 d, float4_ g, uint32_t i) {
-  if (kind == K_CONTAIN) {
-    if (h.hitIdx < 0 && contains_exact(g, o)) h.hitIdx = (int)i;
-  } else {
-    float t;
-    if (ray_sphere_exact(g, o, d, t)) {
-      if (t < h.minT) { h.minT = t; h.hitIdx = (int)i; }   /* strict: first index wins ties */
-    }
+/* ---- exact resolution of one candidate ---------------------------------------- */
+/* Trace ray: running closest hit (raytracer.h:166-188; strict <: first index wins ties). */
+RT_HD void resolve_trace(float& minT, int& hitIdx, V3 o, V3 d, float4_ g, uint32_t i) {
+  float t;
+  if (ray_sphere_exact(g, o, d, t)) {
+    if (t < minT) { minT = t; hitIdx = (int)i; }
   }
-  return h;
 }
-RT_HD void resolve_candidate(Lane& L, const SceneView& sc, uint32_t i) {
-  if (i >= sc.n) return;
-  L.ctr.exactTests++;
-  HitAcc h; h.minT = L.minT; h.hitIdx = L.hitIdx;
-  h = resolve_one(h, L.kind, query_origin(L.qy), mk(L.qy.dx, L.qy.dy, L.qy.dz), sc.geo[i], i);
-  L.minT = h.minT; L.hitIdx = h.hitIdx;
+/* Shadow ray towards a light at squared distance `gap`: occluded iff the closest hit with
+ * t < 1000 has |t d|^2 < gap (raytracer.h:291-304).  |t d|^2 is monotone in t, so "some hit
+ * with t < 1000 and |t d|^2 < gap" is the same predicate (SURVEY.md §8a note 7). */
+RT_HD bool resolve_shadow(V3 o, V3 d, float gap, float4_ g) {
+  float t;
+  if (ray_sphere_exact(g, o, d, t) && t < 1000.f) {
+    const V3 dist = vscale(t, d);
+    return vdot(dist, dist) < gap;
+  }
+  return false;
+}
+/* Containment probe: first containing sphere in index order (raytracer.h:255-267). */
+RT_HD void resolve_contain(int& hitIdx, V3 p, float4_ g, uint32_t i) {
+  if (hitIdx < 0 && contains_exact(g, p)) hitIdx = (int)i;
 }
 
 }  // namespace rtg

@@ -1,24 +1,28 @@
 /* rt_kernels.cuh — sm_100a kernels of the trace loop.
  *
- * trace_kernel     persistent CTAs, one lane = one pixel in flight.  Replaces
- *                  `__kernel raytrace` (raytrace_kernel.cl:870-973) and the CPU
- *                  pixel loop (main.cpp:404-453).
+ * trace_kernel     persistent CTAs; every lane owns NSLOTS pixels in flight.  Replaces
+ *                  `__kernel raytrace` (raytrace_kernel.cl:870-973) and the CPU pixel
+ *                  loop (main.cpp:404-453).
  * pack_kernel      float4 framebuffer -> packed Vec[W*H] (the reference's dst layout)
  * quantise_kernel  float4 framebuffer + max -> RGB8 (main.cpp:71-76)
+ * assemble_rgb8_kernel  multi-GPU strip de-interleave
  *
- * Loop structure of trace_kernel (per warp, all lanes converged at every step):
- *   refill   lanes without a pixel take the next work items from a tile queue
- *            (global atomicAdd per warp chunk, __ballot_sync ranks the takers)
- *   filter   every lane runs its current query (ray or containment probe)
- *            against ALL spheres: 1 broadcast LDS.128 + 7 FFMA + 1 FSETP + 1 mask
- *            op per sphere, sphere records staged once per CTA into shared memory
- *            by a TMA bulk copy (cp.async.bulk + mbarrier) or read from
- *            __constant__ for small scenes
- *   gather   lanes whose 32-sphere mask is non-zero append candidate indices to a
- *            per-lane list in shared memory
- *   resolve  k-th candidate of every lane is put through the reference's exact
- *            expressions together (convergent)
- *   advance  O(1) shading / state transition (divergent by query kind, short)
+ * One pass of trace_kernel (per warp, all lanes converged throughout):
+ *   refill   free slots take the next pixels from a tile queue (one global atomicAdd
+ *            per warp granule, __ballot_sync ranks the takers)
+ *   vote     every lane reports which query kinds its slots are waiting on; the warp
+ *            picks the kind that fills most lanes (__reduce_add_sync)
+ *   filter   the chosen kind's loop over ALL spheres, sphere records staged once per
+ *            CTA into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier) or
+ *            read from __constant__ for small scenes:
+ *              trace    2 rays per lane    (1 LDS.128 + 2 x [7 FFMA + FADD + SHF]) per sphere
+ *              shadow   4 rays, one origin (1 LDS.128 + 3 FFMA + 4 x [4 FFMA + FADD + SHF])
+ *              contain  2 probes per lane  (1 LDS.128 + 2 x [3 FFMA + FADD + SHF])
+ *            each test leaves one SIGN BIT (certain miss or not) in a funnel-shifted mask
+ *   gather   set bits become (sub-query, sphere) entries in a per-lane shared-memory list
+ *   resolve  k-th entries of all lanes go through the reference's exact expressions together
+ *   advance  the served slots take their O(1) shading / state transition (one kind per
+ *            pass, so the lanes agree on the path)
  */
 #ifndef RT_KERNELS_CUH
 #define RT_KERNELS_CUH
@@ -30,9 +34,10 @@
 namespace rtg {
 
 #define RT_BLOCK 256
-#define RT_LIST_MAX 8
+#define RT_LIST_MAX 24
 #define RT_CONST_MAX_SPHERES 1024
-#define RT_NUM_COUNTERS 10
+#define RT_NUM_COUNTERS 12
+#define RT_NO_PIXEL 0xFFFFFFFFu
 
 struct TraceParams {
   SceneView sc;
@@ -40,11 +45,12 @@ struct TraceParams {
   float4* fb;               /* [localRows*W] {r,g,b,1}                              */
   unsigned int* workCounter;/* tile queue head                                      */
   unsigned int* maxBits;    /* running max of positive channel values (float bits)  */
-  unsigned long long* counters;  /* [RT_NUM_COUNTERS] rays, shadow, containQ, containT, exact, samples, lane-iters, active-lane-iters, null rays */
+  unsigned long long* counters;  /* [RT_NUM_COUNTERS], see rt_shim.cu                */
   uint32_t localRows;       /* rows rendered by this context                        */
   uint32_t stripRows, stripFirst, stripStride;   /* row r is ours iff (r/stripRows)%stripStride==stripFirst */
   uint32_t tilesX, totalWork, chunk;
   int noFilter;             /* debug: exact test for every sphere                   */
+  int prefetch;             /* prefetch served slots' state into L1 before the sphere loop */
 };
 
 __constant__ float4_ c_filt[RT_CONST_MAX_SPHERES];
@@ -98,30 +104,312 @@ __device__ __forceinline__ bool work_to_pixel(const TraceParams& p, uint32_t idx
   return true;
 }
 
-/* List overflow (more than RT_LIST_MAX candidates for one query): resolve what is queued.
- * Rare and divergent, so it is kept out of line (and by value, so the lane state stays in
- * registers) to keep the filter loop small. */
-__device__ __noinline__ HitAcc flush_list(HitAcc h, int kind, V3 o, V3 d, const float4_* geo,
-                                          uint32_t n, const unsigned short* sList, uint32_t tid) {
-#pragma unroll 1
-  for (int k = 0; k < RT_LIST_MAX; ++k) {
-    const uint32_t i = sList[k * RT_BLOCK + tid];
-    if (i < n) h = resolve_one(h, kind, o, d, geo[i], i);
+/* Per-warp state shared by the passes. */
+struct WarpCtx {
+  const float4* filt;       /* filter records (shared memory, or unused with __constant__) */
+  unsigned short* list;     /* per-lane candidate lists: list[k * RT_BLOCK + tid]          */
+  uint32_t tid;
+  uint32_t nPad;
+};
+
+template <bool USE_CONST>
+__device__ __forceinline__ float4_ load_filt(const WarpCtx& w, uint32_t i) {
+  float4_ s;
+  if (USE_CONST) {
+    s = c_filt[i];
+  } else {
+    const float4 v = w.filt[i];
+    s.x = v.x; s.y = v.y; s.z = v.z; s.w = v.w;
   }
-  return h;
+  return s;
 }
 
-template <bool USE_CONST, int MIN_BLOCKS, int GROUP>
+/* Spheres per unrolled group of each pass.  Small groups keep the three hot loops inside
+ * the instruction caches (they run concurrently on one SM in different warps). */
+#ifndef RT_GROUP_T
+#define RT_GROUP_T 8
+#endif
+#ifndef RT_GROUP_S
+#define RT_GROUP_S 4
+#endif
+#ifndef RT_GROUP_C
+#define RT_GROUP_C 8
+#endif
+
+/* Turn the set bits of one group's combined candidate mask into list entries
+ * (sub << 14 | sphere).  Sub-query `sub` owns bits [sub*BITS, sub*BITS+G); inside a field
+ * bit (G-1-j) belongs to sphere base+j, so scanning from the top bit yields each
+ * sub-query's spheres in increasing order.  A full list sets `overflow`: that lane then
+ * resolves the pass exactly against every sphere (rare). */
+template <int BITS, int G>
+__device__ __forceinline__ void gather(const WarpCtx& w, unsigned comb, uint32_t base, int& cnt,
+                                       bool& overflow) {
+  while (comb) {
+    const int b = 31 - __clz(comb);
+    comb &= ~(1u << b);
+    if (cnt < RT_LIST_MAX) {
+      const uint32_t sub = (uint32_t)b / BITS, j = (uint32_t)(G - 1) - ((uint32_t)b % BITS);
+      w.list[cnt * RT_BLOCK + w.tid] = (unsigned short)((sub << 14) | (base + j));
+      ++cnt;
+    } else {
+      overflow = true;
+    }
+  }
+}
+
+#define RT_FULL 0xFFFFFFFFu
+
+/* Cold path (list overflow, non-finite geometry, no_filter debug mode): answer the slot's
+ * pending query with the exact test against every sphere.  Out of line; returns the
+ * number of exact tests. */
+__device__ __noinline__ uint32_t exact_all(const SceneView sc, Slot* s, unsigned subs) {
+  uint32_t tests = 0;
+  if (s->kind == K_TRACE) {
+    float t = 1000.f; int h = -1;
+    DirQ D;
+    if (make_dir(D, s->qo, s->qd[0])) {
+      for (uint32_t i = 0; i < sc.n; ++i) resolve_trace(t, h, s->qo, s->qd[0], sc.geo[i], i);
+      tests = sc.n;
+    }
+    s->minT = t; s->hitIdx = h;
+  } else if (s->kind == K_SHADOW) {
+    unsigned blocked = s->blocked;
+    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+      if ((subs >> k) & 1u) {
+        blocked &= ~(1u << k);
+        for (uint32_t i = 0; i < sc.n; ++i) {
+          ++tests;
+          if (resolve_shadow(s->qo, s->qd[k], s->gap[k], sc.geo[i])) { blocked |= 1u << k; break; }
+        }
+      }
+    }
+    s->blocked = blocked;
+  } else if (s->kind == K_CONTAIN) {
+    int h = -1;
+    for (uint32_t i = 0; i < sc.n && h < 0; ++i) { ++tests; resolve_contain(h, s->qo, sc.geo[i], i); }
+    s->hitIdx = h;
+  }
+  return tests;
+}
+
+/* ---- trace pass: up to two rays per lane ---------------------------------------- */
+template <bool USE_CONST>
+__device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& w, Slot* slots, int s0,
+                                           int s1, Counters& ctr) {
+  constexpr int G = RT_GROUP_T;
+  static_assert(G <= 16, "two 16-bit mask fields");
+  OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
+  DirQ D0, D1;
+  D0.ndx = D0.ndy = D0.ndz = D0.od = 0.f; D1 = D0;
+  bool live0 = false, live1 = false, exact0 = false, exact1 = false;
+  if (s0 >= 0) {
+    O0 = make_origin(slots[s0].qo);
+    live0 = make_dir(D0, slots[s0].qo, slots[s0].qd[0]);
+    exact0 = live0 && (p.noFilter || !(origin_filterable(O0) && dir_filterable(D0)));
+  }
+  if (s1 >= 0) {
+    O1 = make_origin(slots[s1].qo);
+    live1 = make_dir(D1, slots[s1].qo, slots[s1].qd[0]);
+    exact1 = live1 && (p.noFilter || !(origin_filterable(O1) && dir_filterable(D1)));
+  }
+  const unsigned fld = (1u << G) - 1u;
+  const unsigned msk = ((live0 && !exact0) ? fld : 0u) | ((live1 && !exact1) ? (fld << 16) : 0u);
+  int cnt = 0;
+  bool overflow = false;
+  if (!p.noFilter) {
+    const uint32_t groups = w.nPad / G;
+    for (uint32_t g = 0; g < groups; ++g) {
+      unsigned k0 = 0, k1 = 0;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const float4_ s = load_filt<USE_CONST>(w, g * G + j);
+        k0 = __funnelshift_l(__float_as_uint(filter_ray(O0, D0, filter_ch(O0, s), s)), k0, 1);
+        k1 = __funnelshift_l(__float_as_uint(filter_ray(O1, D1, filter_ch(O1, s), s)), k1, 1);
+      }
+      const unsigned comb = ~(k0 | (k1 << 16)) & msk;
+      if (comb) gather<16, G>(w, comb, g * G, cnt, overflow);
+    }
+  }
+  float t0 = 1000.f, t1 = 1000.f;
+  int h0 = -1, h1 = -1;
+  const int maxc = __reduce_max_sync(RT_FULL, cnt);
+#pragma unroll 1
+  for (int k = 0; k < maxc; ++k) {
+    if (k < cnt && !overflow) {
+      const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+      const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+      if (i < p.sc.n) {
+        ctr.exactTests++;
+        const Slot& q = slots[sub ? s1 : s0];
+        const float t = ray_sphere_t(p.sc.geo[i], q.qo, q.qd[0]);
+        if (t > 0.f) {       /* raytracer.h:166-188; strict <: first index wins ties */
+          if (sub) { if (t < t1) { t1 = t; h1 = (int)i; } }
+          else     { if (t < t0) { t0 = t; h0 = (int)i; } }
+        }
+      }
+    }
+  }
+  if (overflow) { exact0 = live0; exact1 = live1; }
+  if (s0 >= 0) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
+  if (s1 >= 0) { slots[s1].minT = t1; slots[s1].hitIdx = h1; }
+  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
+  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+}
+
+/* ---- shadow pass: the (up to four) shadow rays of one hit share their origin ------ */
+template <bool USE_CONST, int ND>
+__device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx& w, Slot* slots, int s0,
+                                            Counters& ctr) {
+  constexpr int G = RT_GROUP_S;
+  static_assert(G * ND <= 32, "ND mask fields of G bits");
+  OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
+  DirQ D[ND];
+  unsigned live = 0u, exact = 0u;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; }
+  if (s0 >= 0) {
+    O = make_origin(slots[s0].qo);
+    const bool ofil = origin_filterable(O);
+    const int nd = slots[s0].ndirs;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      if (k < nd && make_dir(D[k], slots[s0].qo, slots[s0].qd[k])) {
+        live |= 1u << k;
+        if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
+      }
+    }
+  }
+  unsigned msk = 0u;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) msk |= (((live & ~exact) >> k) & 1u) ? (((1u << G) - 1u) << (k * G)) : 0u;
+  int cnt = 0;
+  bool overflow = false;
+  if (!p.noFilter) {
+    const uint32_t groups = w.nPad / G;
+    for (uint32_t g = 0; g < groups; ++g) {
+      unsigned sk[ND];
+#pragma unroll
+      for (int k = 0; k < ND; ++k) sk[k] = 0u;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const float4_ s = load_filt<USE_CONST>(w, g * G + j);
+        const float ch = filter_ch(O, s);
+#pragma unroll
+        for (int k = 0; k < ND; ++k)
+          sk[k] = __funnelshift_l(__float_as_uint(filter_ray(O, D[k], ch, s)), sk[k], 1);
+      }
+      unsigned comb = 0u;
+#pragma unroll
+      for (int k = 0; k < ND; ++k) comb |= sk[k] << (k * G);
+      comb = ~comb & msk;
+      if (comb) gather<G, G>(w, comb, g * G, cnt, overflow);
+    }
+  }
+  unsigned blocked = 0u;
+  const int maxc = __reduce_max_sync(RT_FULL, cnt);
+#pragma unroll 1
+  for (int k = 0; k < maxc; ++k) {
+    if (k < cnt && !overflow) {
+      const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+      const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+      if (i < p.sc.n && !((blocked >> sub) & 1u)) {
+        ctr.exactTests++;
+        if (resolve_shadow(slots[s0].qo, slots[s0].qd[sub], slots[s0].gap[sub], p.sc.geo[i])) blocked |= 1u << sub;
+      }
+    }
+  }
+  if (overflow) exact = live;
+  if (s0 >= 0) slots[s0].blocked = blocked;
+  if (exact) ctr.exactTests += exact_all(p.sc, &slots[s0], exact);
+}
+
+/* ---- containment pass: up to two probe points per lane ---------------------------- */
+template <bool USE_CONST>
+__device__ __forceinline__ void pass_contain(const TraceParams& p, const WarpCtx& w, Slot* slots, int s0,
+                                             int s1, Counters& ctr) {
+  constexpr int G = RT_GROUP_C;
+  static_assert(G <= 16, "two 16-bit mask fields");
+  OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
+  bool exact0 = false, exact1 = false;
+  if (s0 >= 0) { O0 = make_origin(slots[s0].qo); exact0 = p.noFilter || !origin_filterable(O0); }
+  if (s1 >= 0) { O1 = make_origin(slots[s1].qo); exact1 = p.noFilter || !origin_filterable(O1); }
+  const unsigned fld = (1u << G) - 1u;
+  const unsigned msk = ((s0 >= 0 && !exact0) ? fld : 0u) | ((s1 >= 0 && !exact1) ? (fld << 16) : 0u);
+  int cnt = 0;
+  bool overflow = false;
+  if (!p.noFilter) {
+    const uint32_t groups = w.nPad / G;
+    for (uint32_t g = 0; g < groups; ++g) {
+      unsigned k0 = 0, k1 = 0;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const float4_ s = load_filt<USE_CONST>(w, g * G + j);
+        k0 = __funnelshift_l(__float_as_uint(filter_point(O0, filter_ch(O0, s))), k0, 1);
+        k1 = __funnelshift_l(__float_as_uint(filter_point(O1, filter_ch(O1, s))), k1, 1);
+      }
+      const unsigned comb = ~(k0 | (k1 << 16)) & msk;
+      if (comb) gather<16, G>(w, comb, g * G, cnt, overflow);
+    }
+  }
+  int h0 = -1, h1 = -1;
+  const int maxc = __reduce_max_sync(RT_FULL, cnt);
+#pragma unroll 1
+  for (int k = 0; k < maxc; ++k) {
+    if (k < cnt && !overflow) {
+      const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+      const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+      if (i < p.sc.n) {
+        ctr.exactTests++;
+        const bool in = contains_exact(p.sc.geo[i], slots[sub ? s1 : s0].qo);
+        if (in) {            /* raytracer.h:264: the first container in index order wins */
+          if (sub) { if (h1 < 0) h1 = (int)i; }
+          else     { if (h0 < 0) h0 = (int)i; }
+        }
+      }
+    }
+  }
+  if (overflow) { exact0 = s0 >= 0; exact1 = s1 >= 0; }
+  if (s0 >= 0) slots[s0].hitIdx = h0;
+  if (s1 >= 0) slots[s1].hitIdx = h1;
+  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
+  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+}
+
+/* Pull the state words of a slot that is about to be served into L1 while the sphere loop
+ * runs: the per-lane slots live in local memory (one 128-byte line per word per warp), far
+ * more than L1 holds across all resident warps, so without this the O(1) code after the loop
+ * waits on L2 for every field it touches. */
+__device__ __forceinline__ void prefetch_slot(const Slot& s) {
+  const float* w = reinterpret_cast<const float*>(&s);
+  constexpr int WORDS = (int)((sizeof(Slot) - sizeof(Frame) * RT_MAX_STACK) / sizeof(float));
+#pragma unroll 1
+  for (int i = 0; i < WORDS; ++i)
+    asm volatile("{ .reg .u64 la; cvta.to.local.u64 la, %0; prefetch.local.L1 [la]; }" ::"l"(w + i));
+}
+
+/* Advance one served slot; store the pixel when it completes. */
+__device__ __forceinline__ void advance_slot(const TraceParams& p, Slot& s, Counters& ctr, float& laneMax) {
+  if (advance(s, ctr, p.sc, p.cam)) {
+    if (finish_sample(s, ctr, p.cam)) {
+      p.fb[s.pixel] = make_float4(s.acc.x, s.acc.y, s.acc.z, 1.f);
+      if (s.acc.x > laneMax) laneMax = s.acc.x;   /* algebra.h:74-82, NaN skipped */
+      if (s.acc.y > laneMax) laneMax = s.acc.y;
+      if (s.acc.z > laneMax) laneMax = s.acc.z;
+      s.pixel = RT_NO_PIXEL;
+      s.kind = K_NULL;
+    }
+  }
+}
+
+template <bool USE_CONST, int MIN_BLOCKS, int NSLOTS>
 __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const TraceParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
   /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists] */
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float4* sFilt = reinterpret_cast<float4*>(smem_raw + 16);
   const uint32_t filtBytes = USE_CONST ? 0u : p.sc.nPad * 16u;
-  unsigned short* sList = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
-  const unsigned FULL = 0xFFFFFFFFu;
 
   if (!USE_CONST) {
     if (tid == 0) {
@@ -129,7 +417,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
       asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     __syncthreads();
-    if (tid == 0) {
+    if (tid == 0 && filtBytes) {
       mbar_expect_tx(bar, filtBytes);
       const unsigned char* src = reinterpret_cast<const unsigned char*>(p.sc.filt);
       unsigned char* dstp = reinterpret_cast<unsigned char*>(sFilt);
@@ -138,159 +426,125 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
         tma_bulk_g2s(dstp + off, src + off, n, bar);
       }
     }
-    mbar_wait(bar, 0);
+    if (filtBytes) mbar_wait(bar, 0);
   }
 
-  Lane L;
-  Frame stack[RT_MAX_STACK];
-  L.kind = K_NULL;
-  query_null(L.qy);
-  L.pixel = 0xFFFFFFFFu;
-  L.minT = 1000.f; L.hitIdx = -1;
-  L.top = -1;
-  L.ctr.rays = L.ctr.shadow = L.ctr.containQ = L.ctr.containT = L.ctr.exactTests = L.ctr.samples = 0;
-  L.ctr.nullRays = 0;
-  L.medium = (int)p.sc.n; L.obj = 0; L.light = 0;
+  WarpCtx w;
+  w.filt = sFilt;
+  w.list = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
+  w.tid = tid;
+  w.nPad = p.sc.nPad;
+
+  Slot slots[NSLOTS];
+#pragma unroll 1
+  for (int k = 0; k < NSLOTS; ++k) { slots[k].kind = K_NULL; slots[k].pixel = RT_NO_PIXEL; slots[k].ndirs = 0; }
+  Counters ctr;
+  ctr.rays = ctr.shadow = ctr.containQ = ctr.containT = ctr.exactTests = ctr.samples = ctr.nullRays = 0;
   float laneMax = 0.f;
-  uint32_t laneIters = 0, activeIters = 0;
+  uint32_t passT = 0, passS2 = 0, passS4 = 0, passC = 0;   /* passes by kind (warp-uniform) */
+  uint32_t servedT = 0, servedS = 0, servedC = 0;            /* sub-queries of this lane served */
 
-  uint32_t wbase = 0, wend = 0;   /* warp-uniform slice of the tile queue */
+  uint32_t wbase = 0, wend = 0;          /* warp-uniform slice of the tile queue */
   bool queueDry = false;
-
-  const uint32_t groups = p.sc.nPad / GROUP;   /* nPad is a multiple of 32 */
 
   for (;;) {
     /* ---- refill ---- */
-    bool need = (L.pixel == 0xFFFFFFFFu);
-    while (!queueDry) {
-      const unsigned m = __ballot_sync(FULL, need);
-      if (m == 0) break;
-      if (wbase >= wend) {
-        uint32_t b = 0;
-        if (lane == 0) b = atomicAdd(p.workCounter, p.chunk);
-        b = __shfl_sync(FULL, b, 0);
-        if (b >= p.totalWork) { queueDry = true; break; }
-        wbase = b;
-        wend = (b + p.chunk < p.totalWork) ? b + p.chunk : p.totalWork;
-      }
-      const uint32_t avail = wend - wbase;
-      const uint32_t rank = __popc(m & ((1u << lane) - 1u));
-      if (need && rank < avail) {
-        uint32_t gx, gy, dst;
-        if (work_to_pixel(p, wbase + rank, gx, gy, dst)) {
-          if (start_pixel(L, p.cam, gx, gy, dst)) {
-            need = false;
-          } else {
-            /* zero samples: the pixel is black (main.cpp:420, loop never runs) */
-            p.fb[dst] = make_float4(0.f, 0.f, 0.f, 1.f);
-            L.pixel = 0xFFFFFFFFu;
-          }
-        }
-      }
-      const uint32_t cnt = __popc(m);
-      wbase += (cnt < avail) ? cnt : avail;
-    }
-    if (__ballot_sync(FULL, L.kind != K_NULL) == 0) break;
-
-    /* ---- filter + gather ---- */
-    int cnt = 0;
-    laneIters++;
-    if (L.kind != K_NULL) activeIters++;
-    const bool filterable = query_filterable(L.qy);
-    if (!p.noFilter) {
-      for (uint32_t g = 0; g < groups; ++g) {
-        /* bit (GROUP-1-j) of `skip` = sign bit of test j: one FADD + one funnel shift per test */
-        unsigned skip = 0;
-#pragma unroll
-        for (int j = 0; j < GROUP; ++j) {
-          float4 s4;
-          if (USE_CONST) {
-            const float4_ c = c_filt[g * GROUP + j];
-            s4 = make_float4(c.x, c.y, c.z, c.w);
-          } else {
-            s4 = sFilt[g * GROUP + j];
-          }
-          float4_ s; s.x = s4.x; s.y = s4.y; s.z = s4.z; s.w = s4.w;
-          skip = __funnelshift_l(__float_as_uint(filter_diff(L.qy, s)), skip, 1);
-        }
-        unsigned cand = ~skip & (GROUP == 32 ? 0xFFFFFFFFu : ((1u << (GROUP & 31)) - 1u));
-        if (cand) {
-          do {
-            const int b = 31 - __clz(cand);          /* highest bit = lowest sphere index */
-            cand &= ~(1u << b);
-            if (cnt == RT_LIST_MAX) {
-              HitAcc h; h.minT = L.minT; h.hitIdx = L.hitIdx;
-              h = flush_list(h, L.kind, query_origin(L.qy), mk(L.qy.dx, L.qy.dy, L.qy.dz), p.sc.geo,
-                             p.sc.n, sList, tid);
-              L.minT = h.minT; L.hitIdx = h.hitIdx;
-              L.ctr.exactTests += RT_LIST_MAX;
-              cnt = 0;
-            }
-            sList[cnt * RT_BLOCK + tid] = (unsigned short)(g * GROUP + (GROUP - 1 - b));
-            ++cnt;
-          } while (cand);
-        }
-      }
-      /* ---- resolve (convergent over lanes) ---- */
-      if (filterable) {
-        const int maxc = __reduce_max_sync(FULL, cnt);
 #pragma unroll 1
-        for (int k = 0; k < maxc; ++k) {
-          if (k < cnt) resolve_candidate(L, p.sc, sList[k * RT_BLOCK + tid]);
+    for (int k = 0; k < NSLOTS && !queueDry; ++k) {
+      bool need = (slots[k].pixel == RT_NO_PIXEL);
+      while (!queueDry) {
+        const unsigned m = __ballot_sync(RT_FULL, need);
+        if (m == 0) break;
+        if (wbase >= wend) {
+          uint32_t b = 0;
+          if (lane == 0) b = atomicAdd(p.workCounter, p.chunk);
+          b = __shfl_sync(RT_FULL, b, 0);
+          if (b >= p.totalWork) { queueDry = true; break; }
+          wbase = b;
+          wend = (b + p.chunk < p.totalWork) ? b + p.chunk : p.totalWork;
         }
-      } else {
-        /* not reached by any finite scene; keeps NaN/inf geometry on the reference's own path */
-        (void)__reduce_max_sync(FULL, 0);
-        L.minT = 1000.f; L.hitIdx = -1;
-        if (L.kind != K_NULL)
-          for (uint32_t i = 0; i < p.sc.n; ++i) resolve_candidate(L, p.sc, i);
+        const uint32_t avail = wend - wbase;
+        const uint32_t rank = __popc(m & ((1u << lane) - 1u));
+        if (need && rank < avail) {
+          uint32_t gx, gy, dst;
+          if (work_to_pixel(p, wbase + rank, gx, gy, dst)) {
+            if (start_pixel(slots[k], ctr, p.cam, gx, gy, dst)) {
+              need = false;
+            } else {
+              /* zero samples: the pixel is black (main.cpp:420, the loops never run) */
+              p.fb[dst] = make_float4(0.f, 0.f, 0.f, 1.f);
+              slots[k].pixel = RT_NO_PIXEL;
+            }
+          }
+        }
+        const uint32_t cnt = __popc(m);
+        wbase += (cnt < avail) ? cnt : avail;
       }
-    } else {
-      if (L.kind != K_NULL && L.qy.q != INFINITY)
-        for (uint32_t i = 0; i < p.sc.n; ++i) resolve_candidate(L, p.sc, i);
     }
 
-    /* ---- advance ---- */
-    if (L.kind != K_NULL) {
-      if (advance(L, p.sc, stack, p.cam)) {
-        if (finish_sample(L, p.cam)) {
-          p.fb[L.pixel] = make_float4(L.acc.x, L.acc.y, L.acc.z, 1.f);
-          if (L.acc.x > laneMax) laneMax = L.acc.x;   /* algebra.h:74-82, NaN skipped */
-          if (L.acc.y > laneMax) laneMax = L.acc.y;
-          if (L.acc.z > laneMax) laneMax = L.acc.z;
-          L.pixel = 0xFFFFFFFFu;
-          L.kind = K_NULL;
-          query_null(L.qy);
-        }
-      }
+    /* ---- vote ---- */
+    int t0 = -1, t1 = -1, s0 = -1, c0 = -1, c1 = -1, nd = 0;
+#pragma unroll 1
+    for (int k = 0; k < NSLOTS; ++k) {
+      const int kind = slots[k].kind;
+      if (kind == K_TRACE) { if (t0 < 0) t0 = k; else if (t1 < 0) t1 = k; }
+      else if (kind == K_SHADOW) { if (s0 < 0) { s0 = k; nd = slots[k].ndirs; } }
+      else if (kind == K_CONTAIN) { if (c0 < 0) c0 = k; else if (c1 < 0) c1 = k; }
+    }
+    const unsigned nT = __reduce_add_sync(RT_FULL, (unsigned)((t0 >= 0) + (t1 >= 0)));
+    const unsigned nS = __reduce_add_sync(RT_FULL, (unsigned)(s0 >= 0));
+    const unsigned nC = __reduce_add_sync(RT_FULL, (unsigned)((c0 >= 0) + (c1 >= 0)));
+    if ((nT | nS | nC) == 0u) {
+      if (queueDry) break;
+      continue;
+    }
+    /* fill fraction: shadow serves one slot per lane (capacity 32), the others two (64) */
+    int sv0, sv1;
+    const int mode = (2u * nS >= nT && 2u * nS >= nC) ? K_SHADOW : (nT >= nC) ? K_TRACE : K_CONTAIN;
+    sv0 = (mode == K_SHADOW) ? s0 : (mode == K_TRACE) ? t0 : c0;
+    sv1 = (mode == K_SHADOW) ? -1 : (mode == K_TRACE) ? t1 : c1;
+    if (p.prefetch) {
+      if (sv0 >= 0) prefetch_slot(slots[sv0]);
+      if (sv1 >= 0) prefetch_slot(slots[sv1]);
+    }
+    if (mode == K_SHADOW) {
+      const int ndMax = __reduce_max_sync(RT_FULL, nd);
+      if (ndMax <= 2) { pass_shadow<USE_CONST, 2>(p, w, slots, s0, ctr); passS2++; }
+      else            { pass_shadow<USE_CONST, 4>(p, w, slots, s0, ctr); passS4++; }
+      servedS += (unsigned)nd;
+    } else if (mode == K_TRACE) {
+      pass_trace<USE_CONST>(p, w, slots, t0, t1, ctr);
+      passT++; servedT += (unsigned)((t0 >= 0) + (t1 >= 0));
+    } else {
+      pass_contain<USE_CONST>(p, w, slots, c0, c1, ctr);
+      passC++; servedC += (unsigned)((c0 >= 0) + (c1 >= 0));
+    }
+    /* ---- advance the served slots (one code instance, same kind across the warp) ---- */
+#pragma unroll 1
+    for (int r = 0; r < 2; ++r) {
+      const int sv = r ? sv1 : sv0;
+      if (sv >= 0) advance_slot(p, slots[sv], ctr, laneMax);
     }
   }
 
   /* ---- per-warp reductions ---- */
   unsigned mb = __float_as_uint(laneMax);   /* laneMax >= 0: uint order == float order */
-  mb = __reduce_max_sync(FULL, mb);
-  const unsigned r0 = __reduce_add_sync(FULL, L.ctr.rays);
-  const unsigned r1 = __reduce_add_sync(FULL, L.ctr.shadow);
-  const unsigned r2 = __reduce_add_sync(FULL, L.ctr.containQ);
-  unsigned long long ct = L.ctr.containT;
-  for (int o = 16; o > 0; o >>= 1) ct += __shfl_xor_sync(FULL, ct, o);
-  unsigned long long ex = L.ctr.exactTests;
-  for (int o = 16; o > 0; o >>= 1) ex += __shfl_xor_sync(FULL, ex, o);
-  const unsigned r5 = __reduce_add_sync(FULL, L.ctr.samples);
-  const unsigned r8 = __reduce_add_sync(FULL, L.ctr.nullRays);
-  unsigned long long li = laneIters, ai = activeIters;
-  for (int o = 16; o > 0; o >>= 1) { li += __shfl_xor_sync(FULL, li, o); ai += __shfl_xor_sync(FULL, ai, o); }
+  mb = __reduce_max_sync(RT_FULL, mb);
+  unsigned long long v[10];
+  v[0] = ctr.rays; v[1] = ctr.shadow; v[2] = ctr.containQ; v[3] = ctr.containT;
+  v[4] = ctr.exactTests; v[5] = ctr.samples; v[6] = ctr.nullRays;
+  v[7] = servedT; v[8] = servedS; v[9] = servedC;
+#pragma unroll
+  for (int i = 0; i < 10; ++i)
+    for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(RT_FULL, v[i], o);
   if (lane == 0) {
     if (mb) atomicMax(p.maxBits, mb);
-    atomicAdd(&p.counters[0], (unsigned long long)r0);
-    atomicAdd(&p.counters[1], (unsigned long long)r1);
-    atomicAdd(&p.counters[2], (unsigned long long)r2);
-    atomicAdd(&p.counters[3], ct);
-    atomicAdd(&p.counters[4], ex);
-    atomicAdd(&p.counters[5], (unsigned long long)r5);
-    atomicAdd(&p.counters[6], li);
-    atomicAdd(&p.counters[7], ai);
-    atomicAdd(&p.counters[8], (unsigned long long)r8);
+#pragma unroll
+    for (int i = 0; i < 10; ++i) atomicAdd(&p.counters[i], v[i]);
+    /* sub-query capacity offered by this warp's passes (32 lanes x 2 / ND / 2 per pass) */
+    atomicAdd(&p.counters[10], 64ull * passT + 64ull * passS2 + 128ull * passS4 + 64ull * passC);
+    /* filter tests executed per sphere-loop pass, in units of lane-tests per sphere */
+    atomicAdd(&p.counters[11], 1ull * passT + 1ull * passS2 + 1ull * passS4 + 1ull * passC);
   }
 }
 

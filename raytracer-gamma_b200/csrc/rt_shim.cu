@@ -15,8 +15,8 @@
 
 using namespace rtg;
 
-#define RT_DEFAULT_MIN_BLOCKS 2
-#define RT_DEFAULT_GROUP 32
+#define RT_DEFAULT_MIN_BLOCKS 3
+#define RT_DEFAULT_SLOTS 3
 
 struct rt_cuda_ctx {
   int device = 0;
@@ -45,7 +45,7 @@ struct rt_cuda_ctx {
   void* hPinned = nullptr; size_t pinnedCap = 0;
 
   /* options */
-  int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0, group = 0;
+  int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0, slots = 0, prefetch = 0;
 
   /* stats */
   rt_cuda_stats stats{};
@@ -163,7 +163,8 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!ctx || !key) return RT_CUDA_ERR_INVALID_ARG;
   if (!strcmp(key, "staging")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->staging = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
-  if (!strcmp(key, "group")) { if (value != 0 && value != 8 && value != 16 && value != 32) return RT_CUDA_ERR_INVALID_ARG; ctx->group = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "prefetch")) { ctx->prefetch = value ? 1 : 0; return RT_CUDA_OK; }
+  if (!strcmp(key, "slots")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->slots = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "min_blocks")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->minBlocks = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
   return RT_CUDA_ERR_INVALID_ARG;
@@ -251,6 +252,7 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   const uint32_t tilesY = (localRows + 3u) / 4u;
   p.totalWork = p.tilesX * tilesY * 32u;
   p.noFilter = ctx->noFilter;
+  p.prefetch = ctx->prefetch;
 
   /* staging choice: __constant__ broadcast for small scenes, shared memory (TMA bulk) otherwise */
   int staging = ctx->staging;
@@ -258,11 +260,11 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if (staging == 1 && (ctx->n == 0 || ctx->nPad > RT_CONST_MAX_SPHERES)) staging = 2;
   const bool useConst = (staging == 1);
   const size_t smem = 16 + (useConst ? 0 : (size_t)ctx->nPad * 16) + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short);
-  /* register budget variant: MIN_BLOCKS resident CTAs per SM (2: 128 regs, 3: 80, 4: 64) */
-  int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
+  /* variants: MIN_BLOCKS resident CTAs per SM (register budget), NSLOTS pixels in flight per lane */
+  const int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
+  const int nslots = ctx->slots ? ctx->slots : RT_DEFAULT_SLOTS;
   void (*kern)(const TraceParams) = nullptr;
-  const int group = ctx->group ? ctx->group : RT_DEFAULT_GROUP;
-#define RT_PICK(C, M) ((group == 8) ? trace_kernel<C, M, 8> : (group == 16) ? trace_kernel<C, M, 16> : trace_kernel<C, M, 32>)
+#define RT_PICK(C, M) ((nslots == 2) ? trace_kernel<C, M, 2> : (nslots == 3) ? trace_kernel<C, M, 3> : trace_kernel<C, M, 4>)
   if (useConst) kern = (minBlocks == 2) ? RT_PICK(true, 2) : (minBlocks == 3) ? RT_PICK(true, 3) : RT_PICK(true, 4);
   else          kern = (minBlocks == 2) ? RT_PICK(false, 2) : (minBlocks == 3) ? RT_PICK(false, 3) : RT_PICK(false, 4);
 #undef RT_PICK
@@ -406,9 +408,11 @@ extern "C" int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out) {
   CU(cudaMemcpy(c, ctx->dCounters, sizeof c, cudaMemcpyDeviceToHost));
   rt_cuda_stats& s = ctx->stats;
   s.rays = c[0]; s.shadow_rays = c[1]; s.contain_queries = c[2]; s.contain_tests = c[3];
-  s.exact_tests = c[4]; s.samples = c[5]; s.lane_iters = c[6]; s.active_lane_iters = c[7];
-  s.null_rays = c[8];
-  s.filter_tests = ctx->noFilter ? 0 : c[6] * (unsigned long long)ctx->nPad;
+  s.exact_tests = c[4]; s.samples = c[5]; s.null_rays = c[6];
+  s.lane_iters = c[10];                         /* sub-query capacity of all sphere passes    */
+  s.active_lane_iters = c[7] + c[8] + c[9];     /* sub-queries actually served (trace/shadow/contain) */
+  s.served_trace = c[7]; s.served_shadow = c[8]; s.served_contain = c[9]; s.passes = c[11];
+  s.filter_tests = ctx->noFilter ? 0 : c[10] * (unsigned long long)ctx->nPad;
   s.sph_num = ctx->n; s.sph_padded = ctx->nPad; s.lgt_num = ctx->nl;
   s.width = ctx->W; s.height = ctx->H; s.local_rows = ctx->localRows;
   s.kernel_ms = 0.f;

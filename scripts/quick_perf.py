@@ -10,16 +10,15 @@ r = pkg.Renderer(0)
 print("ffma_peak TFLOP/s:", [round(r.ffma_peak(8192), 2) for _ in range(3)])
 cases = [
     ("default 1080p a1 s4", pkg.default_scene(), 1920, 1080, 1.0, 4, {}),
-    ("synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {}),
-    ("synth256 4K a1 s6 g16", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"group": 16}),
     ("synth256 4K a1 s6 mb3", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 3}),
-    ("synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {}),
-    ("synth1024 4K a1 s8 g16", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"group": 16}),
-    ("synth1024 4K a1 s8 g8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"group": 8}),
+    ("synth256 4K a1 s6 mb3 nopf", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 3, "prefetch": 0}),
+    ("synth1024 4K a1 s8 mb2", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 2}),
     ("synth1024 4K a1 s8 mb3", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3}),
-    ("synth1024 4K a1 s8 mb3 g16", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "group": 16}),
-    ("synth16 4K a1 s8", pkg.synth_scene(16, 4), 3840, 2160, 1.0, 8, {}),
-    ("synth4096 2K a1 s8", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {}),
+    ("synth1024 4K a1 s8 mb3 nopf", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "prefetch": 0}),
+    ("synth1024 4K a1 s8 mb3 slots4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "slots": 4}),
+    ("synth1024 4K a1 s8 mb4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4}),
+    ("synth1024 4K a1 s8 mb4 slots4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4, "slots": 4}),
+    ("synth4096 2K a1 s8 mb3", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {"min_blocks": 3}),
 ]
 if len(sys.argv) > 1:
     cases = [c for c in cases if any(a in c[0] for a in sys.argv[1:])]
@@ -44,7 +43,7 @@ for name, (sph, lgt), W, H, alias, S, opts in cases:
         "case": name, "ms": round(ms, 3), "Mrays/s": round(st["rays"] / ms / 1e3, 1),
         "Gtests/s": round(tests / ms / 1e6, 1), "TFLOP/s(17)": round(flops / ms / 1e9, 2),
         "frac_74.4": round(flops / ms / 1e9 / 74.4, 3),
-        "lane_util": round(st["active_lane_iters"] / max(1, st["lane_iters"]), 3),
-        "query_per_ray": round(st["active_lane_iters"] / max(1, st["rays"]), 3),
+        "fill": round(st["active_lane_iters"] / max(1, st["lane_iters"]), 3),
+        "served_T/S/C": [st["served_trace"], st["served_shadow"], st["served_contain"]],
         "exact_per_query": round(st["exact_tests"] / max(1, st["active_lane_iters"]), 3),
         "rays": st["rays"], "grid": st["grid"], "smem": st["smem_bytes"], "staging": st["staging"]}))

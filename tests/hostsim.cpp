@@ -1,8 +1,8 @@
-/* hostsim.cpp — CPU lane simulator of the trace machine in rt_core.cuh.
+/* hostsim.cpp — CPU simulator of the trace machine in rt_core.cuh.
  *
  * TEST INFRASTRUCTURE ONLY (built into tests/_build/libhostsim.so by
- * __graft_entry__.build()).  It runs the very same state machine, filter and
- * exact tests the CUDA kernel runs, one lane at a time, so the control flow of
+ * __graft_entry__.build()).  It runs the very same slot state machine, filter and
+ * exact tests the CUDA kernel runs, one pixel at a time, so the control flow of
  * rt_core.cuh can be checked against the oracle on a machine without a GPU.
  * It is not reachable from the product path (librt_cuda.so never links it).
  * Compile with -ffp-contract=off -mfma (fmaf must be a true fused operation). */
@@ -14,6 +14,47 @@
 #include "rt_soa.h"
 
 using namespace rtg;
+
+/* Answer the slot's pending query the way one pass of the kernel does. */
+static void answer(Slot& s, const SceneView& sc, Counters& ctr, bool noFilter) {
+  const OriginQ O = make_origin(s.qo);
+  const bool ofil = origin_filterable(O);
+  if (s.kind == K_TRACE) {
+    DirQ D;
+    s.minT = 1000.f; s.hitIdx = -1;
+    if (!make_dir(D, s.qo, s.qd[0])) return;           /* zero direction: certain miss */
+    const bool fil = !noFilter && ofil && dir_filterable(D);
+    for (uint32_t i = 0; i < (fil ? sc.nPad : sc.n); ++i) {
+      if (fil && filter_ray(O, D, filter_ch(O, sc.filt[i]), sc.filt[i]) < 0.f) continue;
+      if (i >= sc.n) continue;
+      ctr.exactTests++;
+      resolve_trace(s.minT, s.hitIdx, s.qo, s.qd[0], sc.geo[i], i);
+    }
+  } else if (s.kind == K_SHADOW) {
+    s.blocked = 0u;
+    for (int k = 0; k < s.ndirs; ++k) {
+      DirQ D;
+      if (!make_dir(D, s.qo, s.qd[k])) continue;
+      const bool fil = !noFilter && ofil && dir_filterable(D);
+      for (uint32_t i = 0; i < (fil ? sc.nPad : sc.n); ++i) {
+        if (fil && filter_ray(O, D, filter_ch(O, sc.filt[i]), sc.filt[i]) < 0.f) continue;
+        if (i >= sc.n) continue;
+        if ((s.blocked >> k) & 1u) break;
+        ctr.exactTests++;
+        if (resolve_shadow(s.qo, s.qd[k], s.gap[k], sc.geo[i])) s.blocked |= 1u << k;
+      }
+    }
+  } else if (s.kind == K_CONTAIN) {
+    s.hitIdx = -1;
+    const bool fil = !noFilter && ofil;
+    for (uint32_t i = 0; i < (fil ? sc.nPad : sc.n); ++i) {
+      if (fil && filter_point(O, filter_ch(O, sc.filt[i])) < 0.f) continue;
+      if (i >= sc.n) continue;
+      ctr.exactTests++;
+      resolve_contain(s.hitIdx, s.qo, sc.geo[i], i);
+    }
+  }
+}
 
 extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_light* lights,
                               unsigned nl, unsigned W, unsigned H, float zoom, float alias, int S,
@@ -32,28 +73,23 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
   for (long k = 0; k < (long)row_count; ++k) {
     const unsigned gy = row_begin + (unsigned)k * row_step;
     for (unsigned gx = 0; gx < W; ++gx) {
-      Lane L;
-      Frame stack[RT_MAX_STACK];
-      memset(&L, 0, sizeof L);
-      L.medium = (int)sc.n;
+      Slot* sp = new Slot;
+      Slot& s = *sp;
+      memset(&s, 0, sizeof s);
+      Counters ctr; memset(&ctr, 0, sizeof ctr);
       float* px = out + ((size_t)k * W + gx) * 3;
-      if (!start_pixel(L, cam, gx, gy, 0)) { px[0] = px[1] = px[2] = 0.f; continue; }
+      if (!start_pixel(s, ctr, cam, gx, gy, 0)) { px[0] = px[1] = px[2] = 0.f; delete sp; continue; }
       for (;;) {
         c[6]++; c[7]++;
-        if (noFilter) {
-          if (L.qy.q != INFINITY)
-            for (uint32_t i = 0; i < sc.n; ++i) resolve_candidate(L, sc, i);
-        } else {
-          for (uint32_t i = 0; i < sc.nPad; ++i)
-            if (filter_pass(L.qy, sc.filt[i])) resolve_candidate(L, sc, i);
-        }
-        if (advance(L, sc, stack, cam)) {
-          if (finish_sample(L, cam)) break;
+        answer(s, sc, ctr, noFilter != 0);
+        if (advance(s, ctr, sc, cam)) {
+          if (finish_sample(s, ctr, cam)) break;
         }
       }
-      px[0] = L.acc.x; px[1] = L.acc.y; px[2] = L.acc.z;
-      c[0] += L.ctr.rays; c[1] += L.ctr.shadow; c[2] += L.ctr.containQ; c[3] += L.ctr.containT;
-      c[4] += L.ctr.exactTests; c[5] += L.ctr.samples;
+      px[0] = s.acc.x; px[1] = s.acc.y; px[2] = s.acc.z;
+      c[0] += ctr.rays; c[1] += ctr.shadow; c[2] += ctr.containQ; c[3] += ctr.containT;
+      c[4] += ctr.exactTests; c[5] += ctr.samples;
+      delete sp;
     }
   }
   if (counters) memcpy(counters, c, sizeof c);
