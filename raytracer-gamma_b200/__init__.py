@@ -75,6 +75,8 @@ class Stats(ctypes.Structure):
         ("lane_iters", ctypes.c_uint64), ("active_lane_iters", ctypes.c_uint64),
         ("served_trace", ctypes.c_uint64), ("served_shadow", ctypes.c_uint64),
         ("served_contain", ctypes.c_uint64), ("passes", ctypes.c_uint64),
+        ("passes_trace", ctypes.c_uint64), ("passes_shadow2", ctypes.c_uint64),
+        ("passes_shadow4", ctypes.c_uint64), ("passes_contain", ctypes.c_uint64),
         ("filter_tests", ctypes.c_uint64), ("null_rays", ctypes.c_uint64),
         ("sph_num", ctypes.c_uint32), ("sph_padded", ctypes.c_uint32), ("lgt_num", ctypes.c_uint32),
         ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("local_rows", ctypes.c_uint32),

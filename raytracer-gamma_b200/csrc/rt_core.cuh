@@ -119,9 +119,10 @@ struct SceneView {
  * share it.  With no direction (lhs = -q) the same records answer the containment
  * probe of raytracer.h:245-270: -q - ch < 0 <=> |p-c|^2 > r^2 + slack, and the slack
  * exceeds (r+1e-6)^2 - r^2.
- * lhs and ch are finite (or ch = +inf for padding records), and the rounded
- * difference of two such values carries the sign of the exact difference, so the
- * kernel just collects SIGN BITS.  Geometry that is not finite never reaches the
+ * The kernel forms e = -q - ch once per origin and then fma(b, b, e) per ray: e and b are
+ * finite (or e = -inf for padding records), a fused multiply-add rounds once, and a rounded
+ * value carries the sign of the exact one (an exact zero gives +0), so the kernel just
+ * collects SIGN BITS.  Geometry that is not finite never reaches the
  * filter (origin_filterable / dir_filterable): it is tested exactly against every
  * sphere instead.
  */
@@ -159,12 +160,13 @@ RT_HD float filter_ch(const OriginQ& O, float4_ s) {
   ch = fast_fma(O.py, s.y, ch);
   return fast_fma(O.pz, s.z, ch);
 }
-/* Ray test: negative <=> certain miss. */
+/* Ray test: negative <=> certain miss.  e = -q - ch is shared by all rays of one origin. */
 RT_HD float filter_ray(const OriginQ& O, const DirQ& D, float ch, float4_ s) {
   float bq = fast_fma(D.ndx, s.x, D.od);
   bq = fast_fma(D.ndy, s.y, bq);
   bq = fast_fma(D.ndz, s.z, bq);
-  return ex_sub(fast_fma(bq, bq, O.nq), ch);
+  const float e = ex_sub(O.nq, ch);
+  return fast_fma(bq, bq, e);
 }
 /* Containment test: negative <=> certainly outside. */
 RT_HD float filter_point(const OriginQ& O, float ch) { return ex_sub(O.nq, ch); }
@@ -252,8 +254,9 @@ struct Slot {
   /* answer, filled by the sphere pass */
   float minT; int hitIdx; /* closest hit (trace) / first container (probe) */
   uint32_t blocked;       /* shadow batch: bit k = light `light+k` is occluded */
-  Frame stack[RT_MAX_STACK];
 };
+/* The suspended calls of a slot live beside it: Frame stack[RT_MAX_STACK] (only the slot
+ * record is small enough to be copied into registers while it is advanced). */
 
 struct Camera {           /* main.cpp:384-402, evaluated once on the host in float */
   uint32_t W, H;
@@ -343,9 +346,9 @@ RT_HD bool finish_sample(Slot& s, Counters& ctr, const Camera& cam) {
 
 /* Pop suspended calls until one launches a child ray or the stack is empty
  * (raytracer.h:552-628).  Returns true when the sample is finished. */
-RT_HD bool unwind(Slot& s, Counters& ctr, const Camera& cam) {
+RT_HD bool unwind(Slot& s, Frame* stack, Counters& ctr, const Camera& cam) {
   while (s.top >= 0) {
-    Frame& f = s.stack[s.top];
+    Frame& f = stack[s.top];
     --s.top;
     s.colour = vadd(s.result, f.colour);
     if (f.stage == 1.f) {
@@ -391,7 +394,7 @@ enum { ACT_QUERY = 0, ACT_UNWIND = 1, ACT_SHADOW = 2, ACT_MATTE = 3, ACT_NOMATTE
 
 /* After the containment probe: refraction (raytracer.h:642-815), suspend the
  * call (raytracer.h:516-522), launch the refracted child (raytracer.h:524-533). */
-RT_HD int after_contain(Slot& s, Counters& ctr, const SceneView& sc, const Camera& cam) {
+RT_HD int after_contain(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, const Camera& cam) {
   const int target = (s.hitIdx >= 0) ? s.hitIdx : (int)sc.n;
   const float4_ objA = sc.matA[s.obj], objB = sc.matB[s.obj];
   const float4_ medA = sc.matA[s.medium], medB = sc.matB[s.medium];
@@ -451,7 +454,7 @@ RT_HD int after_contain(Slot& s, Counters& ctr, const SceneView& sc, const Camer
 
   /* suspend (always fits: depth <= S-1) */
   ++s.top;
-  Frame& f = s.stack[s.top];
+  Frame& f = stack[s.top];
   f.colour = s.colour; f.stage = 1.f;
   f.reflCol = rc; f.medium = (float)s.medium;
   if (significant(rc)) {
@@ -499,7 +502,7 @@ RT_HD int after_matte(Slot& s, Counters& ctr, const SceneView& sc, bool haveMatt
 /* Advance the slot after its query has been answered (hitIdx/minT or blocked).
  * Returns true when the slot's current SAMPLE is finished (result valid);
  * otherwise the slot holds its next query. */
-RT_HD bool advance(Slot& s, Counters& ctr, const SceneView& sc, const Camera& cam) {
+RT_HD bool advance(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, const Camera& cam) {
   int act;
   if (s.kind == K_TRACE) {
     ctr.rays++;
@@ -545,13 +548,13 @@ RT_HD bool advance(Slot& s, Counters& ctr, const SceneView& sc, const Camera& ca
   } else if (s.kind == K_CONTAIN) {
     /* reference loop iterations (early return at the first container) */
     ctr.containT += (s.hitIdx >= 0) ? (uint32_t)(s.hitIdx + 1) : sc.n;
-    act = after_contain(s, ctr, sc, cam);
+    act = after_contain(s, stack, ctr, sc, cam);
   } else {
     return false;
   }
   if (act >= ACT_MATTE) act = after_matte(s, ctr, sc, act == ACT_MATTE);
   if (act == ACT_SHADOW) { setup_shadow_batch(s, sc); return false; }
-  if (act == ACT_UNWIND) return unwind(s, ctr, cam);
+  if (act == ACT_UNWIND) return unwind(s, stack, ctr, cam);
   return false;
 }
 

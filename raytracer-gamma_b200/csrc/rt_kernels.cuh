@@ -36,7 +36,7 @@ namespace rtg {
 #define RT_BLOCK 256
 #define RT_LIST_MAX 24
 #define RT_CONST_MAX_SPHERES 1024
-#define RT_NUM_COUNTERS 12
+#define RT_NUM_COUNTERS 16
 #define RT_NO_PIXEL 0xFFFFFFFFu
 
 struct TraceParams {
@@ -122,6 +122,33 @@ __device__ __forceinline__ float4_ load_filt(const WarpCtx& w, uint32_t i) {
     s.x = v.x; s.y = v.y; s.z = v.z; s.w = v.w;
   }
   return s;
+}
+
+/* ---- packed FP32 pairs (Blackwell FFMA2 / FADD2) --------------------------------------
+ * sm_100a executes fma.rn.f32x2 as ONE instruction (SASS FFMA2) on a register pair, with a
+ * broadcast form for scalar operands.  The filter loops keep two rays per lane in the two
+ * halves, so every multiply-add of the discriminant is issued once for both: the loops
+ * stop being issue-bound and run against the FP32 pipe itself. */
+typedef unsigned long long f32x2;
+__device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
+__device__ __forceinline__ f32x2 pk1(float x) { return pk(x, x); }
+__device__ __forceinline__ float lo_of(f32x2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
+__device__ __forceinline__ float hi_of(f32x2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
+__device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
+struct Origin2 { f32x2 px, py, pz, nq; };
+struct Dir2 { f32x2 ndx, ndy, ndz, od; };
+__device__ __forceinline__ Origin2 pack_origin(const OriginQ& a, const OriginQ& b) {
+  Origin2 o; o.px = pk(a.px, b.px); o.py = pk(a.py, b.py); o.pz = pk(a.pz, b.pz); o.nq = pk(a.nq, b.nq); return o;
+}
+__device__ __forceinline__ Dir2 pack_dir(const DirQ& a, const DirQ& b) {
+  Dir2 d; d.ndx = pk(a.ndx, b.ndx); d.ndy = pk(a.ndy, b.ndy); d.ndz = pk(a.ndz, b.ndz); d.od = pk(a.od, b.od); return d;
+}
+/* b' = d'.(o - c) for two rays */
+__device__ __forceinline__ f32x2 bq2(const Dir2& D, f32x2 cx, f32x2 cy, f32x2 cz) {
+  f32x2 b = fma2(D.ndx, cx, D.od);
+  b = fma2(D.ndy, cy, b);
+  return fma2(D.ndz, cz, b);
 }
 
 /* Spheres per unrolled group of each pass.  Small groups keep the three hot loops inside
@@ -214,6 +241,8 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& 
   }
   const unsigned fld = (1u << G) - 1u;
   const unsigned msk = ((live0 && !exact0) ? fld : 0u) | ((live1 && !exact1) ? (fld << 16) : 0u);
+  const Origin2 OO = pack_origin(O0, O1);
+  const Dir2 DD = pack_dir(D0, D1);
   int cnt = 0;
   bool overflow = false;
   if (!p.noFilter) {
@@ -223,8 +252,14 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& 
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const float4_ s = load_filt<USE_CONST>(w, g * G + j);
-        k0 = __funnelshift_l(__float_as_uint(filter_ray(O0, D0, filter_ch(O0, s), s)), k0, 1);
-        k1 = __funnelshift_l(__float_as_uint(filter_ray(O1, D1, filter_ch(O1, s), s)), k1, 1);
+        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
+        const f32x2 b = bq2(DD, cx, cy, cz);
+        f32x2 ch = fma2(OO.px, cx, pk1(s.w));
+        ch = fma2(OO.py, cy, ch);
+        ch = fma2(OO.pz, cz, ch);
+        const f32x2 d = fma2(b, b, sub2(OO.nq, ch));     /* both rays: sign set <=> certain miss */
+        k0 = __funnelshift_l(__float_as_uint(lo_of(d)), k0, 1);
+        k1 = __funnelshift_l(__float_as_uint(hi_of(d)), k1, 1);
       }
       const unsigned comb = ~(k0 | (k1 << 16)) & msk;
       if (comb) gather<16, G>(w, comb, g * G, cnt, overflow);
@@ -256,7 +291,9 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& 
   if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
 }
 
-/* ---- shadow pass: the (up to four) shadow rays of one hit share their origin ------ */
+/* ---- shadow pass: the (up to four) shadow rays of one hit share their origin ------
+ * A lane with no shadow batch waiting may bring a TRACE slot instead: a trace ray is the
+ * same query with one direction, so it rides along for free and keeps the lane busy. */
 template <bool USE_CONST, int ND>
 __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx& w, Slot* slots, int s0,
                                             Counters& ctr) {
@@ -265,10 +302,12 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
   OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
   DirQ D[ND];
   unsigned live = 0u, exact = 0u;
+  bool asTrace = false;
 #pragma unroll
   for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; }
   if (s0 >= 0) {
     O = make_origin(slots[s0].qo);
+    asTrace = slots[s0].kind == K_TRACE;
     const bool ofil = origin_filterable(O);
     const int nd = slots[s0].ndirs;
 #pragma unroll
@@ -282,6 +321,10 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
   unsigned msk = 0u;
 #pragma unroll
   for (int k = 0; k < ND; ++k) msk |= (((live & ~exact) >> k) & 1u) ? (((1u << G) - 1u) << (k * G)) : 0u;
+  static_assert(ND % 2 == 0, "rays are processed as packed pairs");
+  Dir2 DP[ND / 2];
+#pragma unroll
+  for (int k = 0; k < ND / 2; ++k) DP[k] = pack_dir(D[2 * k], D[2 * k + 1]);
   int cnt = 0;
   bool overflow = false;
   if (!p.noFilter) {
@@ -293,10 +336,15 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const float4_ s = load_filt<USE_CONST>(w, g * G + j);
-        const float ch = filter_ch(O, s);
+        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
+        const f32x2 e = pk1(ex_sub(O.nq, filter_ch(O, s)));   /* -q - ch: once per sphere, all rays share the origin */
 #pragma unroll
-        for (int k = 0; k < ND; ++k)
-          sk[k] = __funnelshift_l(__float_as_uint(filter_ray(O, D[k], ch, s)), sk[k], 1);
+        for (int k = 0; k < ND / 2; ++k) {
+          const f32x2 b = bq2(DP[k], cx, cy, cz);
+          const f32x2 d = fma2(b, b, e);
+          sk[2 * k] = __funnelshift_l(__float_as_uint(lo_of(d)), sk[2 * k], 1);
+          sk[2 * k + 1] = __funnelshift_l(__float_as_uint(hi_of(d)), sk[2 * k + 1], 1);
+        }
       }
       unsigned comb = 0u;
 #pragma unroll
@@ -306,6 +354,8 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
     }
   }
   unsigned blocked = 0u;
+  float t0 = 1000.f;
+  int h0 = -1;
   const int maxc = __reduce_max_sync(RT_FULL, cnt);
 #pragma unroll 1
   for (int k = 0; k < maxc; ++k) {
@@ -314,12 +364,25 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
       const uint32_t i = e & 0x3FFFu, sub = e >> 14;
       if (i < p.sc.n && !((blocked >> sub) & 1u)) {
         ctr.exactTests++;
-        if (resolve_shadow(slots[s0].qo, slots[s0].qd[sub], slots[s0].gap[sub], p.sc.geo[i])) blocked |= 1u << sub;
+        const Slot& q = slots[s0];
+        const V3 d = q.qd[sub];
+        const float t = ray_sphere_t(p.sc.geo[i], q.qo, d);
+        if (t > 0.f) {
+          if (asTrace) {          /* closest hit, raytracer.h:166-188 */
+            if (t < t0) { t0 = t; h0 = (int)i; }
+          } else if (t < 1000.f) { /* occluder iff |t d|^2 < gap, raytracer.h:291-304 (see resolve_shadow) */
+            const V3 dist = vscale(t, d);
+            if (vdot(dist, dist) < q.gap[sub]) blocked |= 1u << sub;
+          }
+        }
       }
     }
   }
   if (overflow) exact = live;
-  if (s0 >= 0) slots[s0].blocked = blocked;
+  if (s0 >= 0) {
+    if (asTrace) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
+    else slots[s0].blocked = blocked;
+  }
   if (exact) ctr.exactTests += exact_all(p.sc, &slots[s0], exact);
 }
 
@@ -335,6 +398,7 @@ __device__ __forceinline__ void pass_contain(const TraceParams& p, const WarpCtx
   if (s1 >= 0) { O1 = make_origin(slots[s1].qo); exact1 = p.noFilter || !origin_filterable(O1); }
   const unsigned fld = (1u << G) - 1u;
   const unsigned msk = ((s0 >= 0 && !exact0) ? fld : 0u) | ((s1 >= 0 && !exact1) ? (fld << 16) : 0u);
+  const Origin2 OO = pack_origin(O0, O1);
   int cnt = 0;
   bool overflow = false;
   if (!p.noFilter) {
@@ -344,8 +408,12 @@ __device__ __forceinline__ void pass_contain(const TraceParams& p, const WarpCtx
 #pragma unroll
       for (int j = 0; j < G; ++j) {
         const float4_ s = load_filt<USE_CONST>(w, g * G + j);
-        k0 = __funnelshift_l(__float_as_uint(filter_point(O0, filter_ch(O0, s))), k0, 1);
-        k1 = __funnelshift_l(__float_as_uint(filter_point(O1, filter_ch(O1, s))), k1, 1);
+        f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
+        ch = fma2(OO.py, pk1(s.y), ch);
+        ch = fma2(OO.pz, pk1(s.z), ch);
+        const f32x2 d = sub2(OO.nq, ch);                  /* both probes: sign set <=> certainly outside */
+        k0 = __funnelshift_l(__float_as_uint(lo_of(d)), k0, 1);
+        k1 = __funnelshift_l(__float_as_uint(hi_of(d)), k1, 1);
       }
       const unsigned comb = ~(k0 | (k1 << 16)) & msk;
       if (comb) gather<16, G>(w, comb, g * G, cnt, overflow);
@@ -387,9 +455,14 @@ __device__ __forceinline__ void prefetch_slot(const Slot& s) {
     asm volatile("{ .reg .u64 la; cvta.to.local.u64 la, %0; prefetch.local.L1 [la]; }" ::"l"(w + i));
 }
 
-/* Advance one served slot; store the pixel when it completes. */
-__device__ __forceinline__ void advance_slot(const TraceParams& p, Slot& s, Counters& ctr, float& laneMax) {
-  if (advance(s, ctr, p.sc, p.cam)) {
+/* Advance one served slot; store the pixel when it completes.  The slot record is copied
+ * into registers first (one batch of independent local loads instead of a dependent
+ * load/store chain through L2) and written back once.  Returns the slot's new
+ * (kind | ndirs << 4) tag for the lane's register-resident census. */
+__device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, Slot* slot, Frame* stack, Counters& ctr,
+                                                 float& laneMax) {
+  Slot s = *slot;
+  if (advance(s, stack, ctr, p.sc, p.cam)) {
     if (finish_sample(s, ctr, p.cam)) {
       p.fb[s.pixel] = make_float4(s.acc.x, s.acc.y, s.acc.z, 1.f);
       if (s.acc.x > laneMax) laneMax = s.acc.x;   /* algebra.h:74-82, NaN skipped */
@@ -397,8 +470,11 @@ __device__ __forceinline__ void advance_slot(const TraceParams& p, Slot& s, Coun
       if (s.acc.z > laneMax) laneMax = s.acc.z;
       s.pixel = RT_NO_PIXEL;
       s.kind = K_NULL;
+      s.ndirs = 0;
     }
   }
+  *slot = s;
+  return (uint32_t)s.kind | ((uint32_t)s.ndirs << 4);
 }
 
 template <bool USE_CONST, int MIN_BLOCKS, int NSLOTS>
@@ -436,8 +512,10 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
   w.nPad = p.sc.nPad;
 
   Slot slots[NSLOTS];
+  Frame stacks[NSLOTS * RT_MAX_STACK];
 #pragma unroll 1
   for (int k = 0; k < NSLOTS; ++k) { slots[k].kind = K_NULL; slots[k].pixel = RT_NO_PIXEL; slots[k].ndirs = 0; }
+  uint32_t tags = 0u;   /* census kept in a register: byte k = kind | ndirs << 4 of slot k */
   Counters ctr;
   ctr.rays = ctr.shadow = ctr.containQ = ctr.containT = ctr.exactTests = ctr.samples = ctr.nullRays = 0;
   float laneMax = 0.f;
@@ -451,7 +529,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
     /* ---- refill ---- */
 #pragma unroll 1
     for (int k = 0; k < NSLOTS && !queueDry; ++k) {
-      bool need = (slots[k].pixel == RT_NO_PIXEL);
+      bool need = (((tags >> (8 * k)) & 0xFu) == (uint32_t)K_NULL);
       while (!queueDry) {
         const unsigned m = __ballot_sync(RT_FULL, need);
         if (m == 0) break;
@@ -470,6 +548,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
           if (work_to_pixel(p, wbase + rank, gx, gy, dst)) {
             if (start_pixel(slots[k], ctr, p.cam, gx, gy, dst)) {
               need = false;
+              tags = (tags & ~(0xFFu << (8 * k))) | (((uint32_t)K_TRACE | (1u << 4)) << (8 * k));
             } else {
               /* zero samples: the pixel is black (main.cpp:420, the loops never run) */
               p.fb[dst] = make_float4(0.f, 0.f, 0.f, 1.f);
@@ -484,34 +563,42 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
 
     /* ---- vote ---- */
     int t0 = -1, t1 = -1, s0 = -1, c0 = -1, c1 = -1, nd = 0;
-#pragma unroll 1
+#pragma unroll
     for (int k = 0; k < NSLOTS; ++k) {
-      const int kind = slots[k].kind;
+      const uint32_t tg = (tags >> (8 * k)) & 0xFFu;
+      const int kind = (int)(tg & 0xFu);
       if (kind == K_TRACE) { if (t0 < 0) t0 = k; else if (t1 < 0) t1 = k; }
-      else if (kind == K_SHADOW) { if (s0 < 0) { s0 = k; nd = slots[k].ndirs; } }
+      else if (kind == K_SHADOW) { if (s0 < 0) { s0 = k; nd = (int)(tg >> 4); } }
       else if (kind == K_CONTAIN) { if (c0 < 0) c0 = k; else if (c1 < 0) c1 = k; }
     }
+    /* a shadow pass also takes one trace ray from lanes that have no shadow batch waiting */
+    const int sOrT = (s0 >= 0) ? s0 : t0;
+    const int ndS = (s0 >= 0) ? nd : (t0 >= 0 ? 1 : 0);
+    const int ndMax = __reduce_max_sync(RT_FULL, nd);
     const unsigned nT = __reduce_add_sync(RT_FULL, (unsigned)((t0 >= 0) + (t1 >= 0)));
-    const unsigned nS = __reduce_add_sync(RT_FULL, (unsigned)(s0 >= 0));
+    const unsigned nS = __reduce_add_sync(RT_FULL, (unsigned)ndS);
     const unsigned nC = __reduce_add_sync(RT_FULL, (unsigned)((c0 >= 0) + (c1 >= 0)));
     if ((nT | nS | nC) == 0u) {
       if (queueDry) break;
       continue;
     }
-    /* fill fraction: shadow serves one slot per lane (capacity 32), the others two (64) */
+    /* serve the kind that fills the largest share of its pass: capacity 64 sub-queries for
+     * trace / contain passes, 32 x (2 or 4) for a shadow pass */
+    const unsigned capS = (ndMax <= 2) ? 64u : 128u;
     int sv0, sv1;
-    const int mode = (2u * nS >= nT && 2u * nS >= nC) ? K_SHADOW : (nT >= nC) ? K_TRACE : K_CONTAIN;
-    sv0 = (mode == K_SHADOW) ? s0 : (mode == K_TRACE) ? t0 : c0;
+    const bool anyS = ndMax > 0;
+    const int mode = (anyS && nS * 64u >= nT * capS && nS * 64u >= nC * capS) ? K_SHADOW
+                     : (nT >= nC) ? K_TRACE : K_CONTAIN;
+    sv0 = (mode == K_SHADOW) ? sOrT : (mode == K_TRACE) ? t0 : c0;
     sv1 = (mode == K_SHADOW) ? -1 : (mode == K_TRACE) ? t1 : c1;
     if (p.prefetch) {
       if (sv0 >= 0) prefetch_slot(slots[sv0]);
       if (sv1 >= 0) prefetch_slot(slots[sv1]);
     }
     if (mode == K_SHADOW) {
-      const int ndMax = __reduce_max_sync(RT_FULL, nd);
-      if (ndMax <= 2) { pass_shadow<USE_CONST, 2>(p, w, slots, s0, ctr); passS2++; }
-      else            { pass_shadow<USE_CONST, 4>(p, w, slots, s0, ctr); passS4++; }
-      servedS += (unsigned)nd;
+      if (ndMax <= 2) { pass_shadow<USE_CONST, 2>(p, w, slots, sv0, ctr); passS2++; }
+      else            { pass_shadow<USE_CONST, 4>(p, w, slots, sv0, ctr); passS4++; }
+      if (s0 >= 0) servedS += (unsigned)nd; else servedT += (unsigned)ndS;
     } else if (mode == K_TRACE) {
       pass_trace<USE_CONST>(p, w, slots, t0, t1, ctr);
       passT++; servedT += (unsigned)((t0 >= 0) + (t1 >= 0));
@@ -523,7 +610,10 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
       const int sv = r ? sv1 : sv0;
-      if (sv >= 0) advance_slot(p, slots[sv], ctr, laneMax);
+      if (sv >= 0) {
+        const uint32_t tg = advance_slot(p, &slots[sv], &stacks[sv * RT_MAX_STACK], ctr, laneMax);
+        tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
+      }
     }
   }
 
@@ -543,8 +633,11 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
     for (int i = 0; i < 10; ++i) atomicAdd(&p.counters[i], v[i]);
     /* sub-query capacity offered by this warp's passes (32 lanes x 2 / ND / 2 per pass) */
     atomicAdd(&p.counters[10], 64ull * passT + 64ull * passS2 + 128ull * passS4 + 64ull * passC);
-    /* filter tests executed per sphere-loop pass, in units of lane-tests per sphere */
     atomicAdd(&p.counters[11], 1ull * passT + 1ull * passS2 + 1ull * passS4 + 1ull * passC);
+    atomicAdd(&p.counters[12], (unsigned long long)passT);
+    atomicAdd(&p.counters[13], (unsigned long long)passS2);
+    atomicAdd(&p.counters[14], (unsigned long long)passS4);
+    atomicAdd(&p.counters[15], (unsigned long long)passC);
   }
 }
 

@@ -73,23 +73,22 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
   for (long k = 0; k < (long)row_count; ++k) {
     const unsigned gy = row_begin + (unsigned)k * row_step;
     for (unsigned gx = 0; gx < W; ++gx) {
-      Slot* sp = new Slot;
-      Slot& s = *sp;
+      Slot s;
+      Frame stack[RT_MAX_STACK];
       memset(&s, 0, sizeof s);
       Counters ctr; memset(&ctr, 0, sizeof ctr);
       float* px = out + ((size_t)k * W + gx) * 3;
-      if (!start_pixel(s, ctr, cam, gx, gy, 0)) { px[0] = px[1] = px[2] = 0.f; delete sp; continue; }
+      if (!start_pixel(s, ctr, cam, gx, gy, 0)) { px[0] = px[1] = px[2] = 0.f; continue; }
       for (;;) {
         c[6]++; c[7]++;
         answer(s, sc, ctr, noFilter != 0);
-        if (advance(s, ctr, sc, cam)) {
+        if (advance(s, stack, ctr, sc, cam)) {
           if (finish_sample(s, ctr, cam)) break;
         }
       }
       px[0] = s.acc.x; px[1] = s.acc.y; px[2] = s.acc.z;
       c[0] += ctr.rays; c[1] += ctr.shadow; c[2] += ctr.containQ; c[3] += ctr.containT;
       c[4] += ctr.exactTests; c[5] += ctr.samples;
-      delete sp;
     }
   }
   if (counters) memcpy(counters, c, sizeof c);
