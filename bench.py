@@ -421,6 +421,13 @@ def run_ours(args):
                           "primaryContainer tests as the reference counts them (SURVEY.md 8d)",
             "kernel_ms": st["kernel_ms"], "traffic": traffic,
             "executed_filter_tests": st["filter_tests"], "exact_tests": st["exact_tests"],
+            # FP32 operations the filter loops really issued (packed FFMA2/FADD2 count 2 lanes x 2 / x 1):
+            # trace pass 30, shadow pass 39 (4 rays) or 23 (2 rays), contain pass 14 flop per lane per sphere
+            "executed_tflops": 32.0 * st["sph_padded"] * (30.0 * st["passes_trace"] + 39.0 * st["passes_shadow4"]
+                                                          + 23.0 * st["passes_shadow2"] + 14.0 * st["passes_contain"])
+                               / (st["kernel_ms"] * 1e-3) / 1e12,
+            "passes": {"trace": st["passes_trace"], "shadow4": st["passes_shadow4"], "shadow2": st["passes_shadow2"],
+                       "contain": st["passes_contain"]},
             "lane_utilisation": st["active_lane_iters"] / max(1, st["lane_iters"]),
             "launch": {"grid": st["grid"], "block": st["block"], "smem_bytes": st["smem_bytes"],
                        "staging": {1: "__constant__", 2: "shared (TMA bulk)"}.get(st["staging"])},

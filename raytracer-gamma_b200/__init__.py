@@ -20,7 +20,7 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = PKG_DIR / "librt_cuda.so"
+LIB_PATH = Path(os.environ.get("RTG_LIB", PKG_DIR / "librt_cuda.so"))   # RTG_LIB: development override
 HOST_BIN = PKG_DIR / "rt_gamma"
 
 # Layout of the reference PODs (sphere.h:9-14, raytracer.h:20-25, vec.h:27-29)

@@ -157,7 +157,7 @@ __device__ __forceinline__ f32x2 bq2(const Dir2& D, f32x2 cx, f32x2 cy, f32x2 cz
 #define RT_GROUP_T 8
 #endif
 #ifndef RT_GROUP_S
-#define RT_GROUP_S 4
+#define RT_GROUP_S 8
 #endif
 #ifndef RT_GROUP_C
 #define RT_GROUP_C 8

@@ -15,8 +15,8 @@
 
 using namespace rtg;
 
-#define RT_DEFAULT_MIN_BLOCKS 3
-#define RT_DEFAULT_SLOTS 3
+#define RT_DEFAULT_MIN_BLOCKS 2
+#define RT_DEFAULT_SLOTS 4
 
 struct rt_cuda_ctx {
   int device = 0;

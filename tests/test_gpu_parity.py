@@ -119,7 +119,8 @@ def test_staging_and_filter_variants_agree(pkg, orc_mod, gpu):
     invisible in the output."""
     sph, lgt = pkg.synth_scene(200, 4, seed=3)
     base, _, st0 = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8)
-    for opts in ({"staging": 1}, {"staging": 2}, {"no_filter": 1}, {"blocks_per_sm": 1}):
+    for opts in ({"staging": 1}, {"staging": 2}, {"no_filter": 1}, {"blocks_per_sm": 1}, {"slots": 2}, {"slots": 3},
+                 {"min_blocks": 3}, {"min_blocks": 4}, {"prefetch": 1}):
         fb, _, st = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8, **opts)
         assert np.array_equal(orc_mod.canon(fb), orc_mod.canon(base)), opts
         assert st["rays"] == st0["rays"]
