@@ -347,6 +347,14 @@ def run_ours(args):
     if G > 1:
         dist.all_reduce(agg, op=dist.ReduceOp.SUM)
         dist.all_reduce(tmax, op=dist.ReduceOp.MAX)
+    per_rank = torch.tensor([kernel_ms, float(st["rays"]), st["active_lane_iters"] / max(1, st["lane_iters"]),
+                             total_ms / args.steps], dtype=torch.float64, device=dev)
+    if G > 1:
+        allr = [torch.zeros_like(per_rank) for _ in range(G)]
+        dist.all_gather(allr, per_rank)
+        per_rank_list = [[round(float(x), 4) for x in t] for t in allr]
+    else:
+        per_rank_list = [[round(float(x), 4) for x in per_rank]]
     rays, live_rays, contain_tests = float(agg[0]), float(agg[1]), float(agg[2])
     total_ms_max, kernel_ms_max = float(tmax[0]), float(tmax[1])
     ms_per_step = total_ms_max / args.steps
@@ -466,6 +474,7 @@ def run_ours(args):
             "frames_per_s": 1e3 / ms_per_step,
             "rays_per_frame": rays, "tflops_17": flops_frame * args.steps / (total_ms_max * 1e-3) / 1e12,
             "trace_kernel_ms_max_over_ranks": kernel_ms_max,
+            "per_rank": {"columns": ["trace_kernel_ms", "rays", "lane_utilisation", "step_ms"], "rows": per_rank_list},
             "wall_s_timed_region": wall,
             "clocks": clocks.report(),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,

@@ -242,7 +242,6 @@ struct Slot {
   int light;              /* first light of the current shadow batch */
   int ndirs;              /* directions in the pending query (1 for a trace ray) */
   float pxw, pyw;
-  V3 acc;                 /* pixel accumulator, main.cpp:420,446 */
   V3 result;              /* "colourSum" of raytracer.h:425 */
   V3 colour, rayD, rayI;  /* the call being evaluated ("currSnapshot") */
   V3 P, Nrm;              /* its hit */
@@ -289,8 +288,17 @@ RT_HD void set_trace_query(Slot& s, Counters& ctr, V3 o, V3 d) {
   if (vdot(d, d) == 0.f) ctr.nullRays++;   /* zero direction: certain miss (see make_dir) */
 }
 
-/* Start the sample (si, sj) of the slot's pixel: main.cpp:432-441 */
-RT_HD void start_sample(Slot& s, Counters& ctr, const Camera& cam) {
+/* Start sample (si, sj) of pixel (gx, gy) of the full frame (main.cpp:409-441): the slot
+ * is one SAMPLE in flight.  Samples of a pixel are independent calls of rayTrace (main.cpp:439);
+ * they are traced as separate work items and summed afterwards in the reference's order
+ * (combine_samples / main.cpp:443-447), which shortens every dependency chain by the sample
+ * count.  `pixel` is the index of the sample's result record. */
+RT_HD void start_task(Slot& s, Counters& ctr, const Camera& cam, uint32_t gx, uint32_t gy,
+                      uint32_t pixel, int si, int sj) {
+  s.pixel = pixel;
+  s.si = si; s.sj = sj;
+  s.pxw = ex_mul(ex_sub((float)gx, ex_mul((float)cam.W, 0.5f)), cam.stepX);
+  s.pyw = ex_mul(ex_sub(ex_mul((float)cam.H, 0.5f), (float)gy), cam.stepY);
   const float x = ex_mul(ex_add(s.pxw, ex_mul((float)s.sj, cam.aliasStep)), cam.aspect);
   const float y = ex_add(s.pyw, ex_mul((float)s.si, cam.aliasStep));
   const V3 d = vunit(mk(x, y, cam.zoom));
@@ -302,18 +310,15 @@ RT_HD void start_sample(Slot& s, Counters& ctr, const Camera& cam) {
   set_trace_query(s, ctr, mk(0.f, 0.f, 0.f), d);
 }
 
-/* Give the slot pixel (gx, gy) of the full frame, stored at dst index `pixel`.
- * Returns false when the pixel needs no samples (alias <= 0: the pixel is black). */
-RT_HD bool start_pixel(Slot& s, Counters& ctr, const Camera& cam, uint32_t gx, uint32_t gy,
-                       uint32_t pixel) {
-  s.pixel = pixel;
-  s.pxw = ex_mul(ex_sub((float)gx, ex_mul((float)cam.W, 0.5f)), cam.stepX);
-  s.pyw = ex_mul(ex_sub(ex_mul((float)cam.H, 0.5f), (float)gy), cam.stepY);
-  s.acc = mk(0.f, 0.f, 0.f);
-  s.si = 0; s.sj = 0;
-  if (cam.nIter <= 0) { s.kind = K_NULL; return false; }
-  start_sample(s, ctr, cam);
-  return true;
+/* The sample's contribution to its pixel: vsmul(currentSample, kSamplesTotinv, ...) main.cpp:443 */
+RT_HD V3 sample_value(const Slot& s, const Camera& cam) { return vscale(cam.inv, s.result); }
+
+/* Sum the nIter x nIter scaled samples of one pixel in the reference's loop order
+ * (i outer, j inner; main.cpp:430-447). */
+RT_HD V3 combine_samples(const V3* samples, int count) {
+  V3 acc = mk(0.f, 0.f, 0.f);
+  for (int k = 0; k < count; ++k) acc = vadd(acc, samples[k]);
+  return acc;
 }
 
 /* raytracer.h:272-286 for the lights light .. light+ndirs-1: shadow rays from P */
@@ -332,16 +337,6 @@ RT_HD void setup_shadow_batch(Slot& s, const SceneView& sc) {
       s.qd[k] = vunit(dir);
     }
   }
-}
-
-/* Sample finished: main.cpp:443-447.  Returns true when the pixel is complete. */
-RT_HD bool finish_sample(Slot& s, Counters& ctr, const Camera& cam) {
-  const V3 v = vscale(cam.inv, s.result);
-  s.acc = vadd(s.acc, v);
-  if (++s.sj >= cam.nIter) { s.sj = 0; ++s.si; }
-  if (s.si >= cam.nIter) return true;
-  start_sample(s, ctr, cam);
-  return false;
 }
 
 /* Pop suspended calls until one launches a child ray or the stack is empty

@@ -43,6 +43,8 @@ struct TraceParams {
   SceneView sc;
   Camera cam;
   float4* fb;               /* [localRows*W] {r,g,b,1}                              */
+  float4* samples;          /* [localRows*W*spp] scaled sample values (spp > 1 only) */
+  uint32_t spp;             /* samples per pixel = nIter * nIter                    */
   unsigned int* workCounter;/* tile queue head                                      */
   unsigned int* maxBits;    /* running max of positive channel values (float bits)  */
   unsigned long long* counters;  /* [RT_NUM_COUNTERS], see rt_shim.cu                */
@@ -89,10 +91,13 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
       : "memory");
 }
 
-/* Map a queue index to a pixel: 8x4 tiles, row-major inside, tiles row-major. */
-__device__ __forceinline__ bool work_to_pixel(const TraceParams& p, uint32_t idx, uint32_t& gx,
-                                              uint32_t& gy, uint32_t& dst) {
-  const uint32_t tile = idx >> 5, within = idx & 31u;
+/* Map a queue index to a work item = one sample of one pixel.  Pixels are walked in 8x4
+ * tiles (row-major inside, tiles row-major); 32 consecutive indices are the 32 pixels of a
+ * tile for one sample, the next 32 the same tile's next sample. */
+__device__ __forceinline__ bool work_to_task(const TraceParams& p, uint32_t idx, uint32_t& gx,
+                                             uint32_t& gy, uint32_t& dst, int& si, int& sj) {
+  const uint32_t grp = idx >> 5, within = idx & 31u;
+  const uint32_t tile = grp / p.spp, k = grp - tile * p.spp;
   const uint32_t ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
   const uint32_t x = tx * 8u + (within & 7u);
   const uint32_t y = ty * 4u + (within >> 3);
@@ -100,7 +105,9 @@ __device__ __forceinline__ bool work_to_pixel(const TraceParams& p, uint32_t idx
   const uint32_t strip = y / p.stripRows;
   gx = x;
   gy = (strip * p.stripStride + p.stripFirst) * p.stripRows + (y - strip * p.stripRows);
-  dst = y * p.cam.W + x;
+  dst = (y * p.cam.W + x) * p.spp + k;
+  si = (int)(k / (uint32_t)p.cam.nIter);
+  sj = (int)(k - (uint32_t)si * (uint32_t)p.cam.nIter);
   return true;
 }
 
@@ -463,15 +470,20 @@ __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, Slot* slo
                                                  float& laneMax) {
   Slot s = *slot;
   if (advance(s, stack, ctr, p.sc, p.cam)) {
-    if (finish_sample(s, ctr, p.cam)) {
-      p.fb[s.pixel] = make_float4(s.acc.x, s.acc.y, s.acc.z, 1.f);
-      if (s.acc.x > laneMax) laneMax = s.acc.x;   /* algebra.h:74-82, NaN skipped */
-      if (s.acc.y > laneMax) laneMax = s.acc.y;
-      if (s.acc.z > laneMax) laneMax = s.acc.z;
-      s.pixel = RT_NO_PIXEL;
-      s.kind = K_NULL;
-      s.ndirs = 0;
+    const V3 v = sample_value(s, p.cam);
+    if (p.spp == 1u) {
+      /* one sample per pixel: the pixel is 0 + sample (main.cpp:420,446) */
+      const V3 a = vadd(mk(0.f, 0.f, 0.f), v);
+      p.fb[s.pixel] = make_float4(a.x, a.y, a.z, 1.f);
+      if (a.x > laneMax) laneMax = a.x;   /* algebra.h:74-82, NaN skipped */
+      if (a.y > laneMax) laneMax = a.y;
+      if (a.z > laneMax) laneMax = a.z;
+    } else {
+      p.samples[s.pixel] = make_float4(v.x, v.y, v.z, 1.f);
     }
+    s.pixel = RT_NO_PIXEL;
+    s.kind = K_NULL;
+    s.ndirs = 0;
   }
   *slot = s;
   return (uint32_t)s.kind | ((uint32_t)s.ndirs << 4);
@@ -545,15 +557,11 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
         const uint32_t rank = __popc(m & ((1u << lane) - 1u));
         if (need && rank < avail) {
           uint32_t gx, gy, dst;
-          if (work_to_pixel(p, wbase + rank, gx, gy, dst)) {
-            if (start_pixel(slots[k], ctr, p.cam, gx, gy, dst)) {
-              need = false;
-              tags = (tags & ~(0xFFu << (8 * k))) | (((uint32_t)K_TRACE | (1u << 4)) << (8 * k));
-            } else {
-              /* zero samples: the pixel is black (main.cpp:420, the loops never run) */
-              p.fb[dst] = make_float4(0.f, 0.f, 0.f, 1.f);
-              slots[k].pixel = RT_NO_PIXEL;
-            }
+          int si, sj;
+          if (work_to_task(p, wbase + rank, gx, gy, dst, si, sj)) {
+            start_task(slots[k], ctr, p.cam, gx, gy, dst, si, sj);
+            need = false;
+            tags = (tags & ~(0xFFu << (8 * k))) | (((uint32_t)K_TRACE | (1u << 4)) << (8 * k));
           }
         }
         const uint32_t cnt = __popc(m);
@@ -639,6 +647,27 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
     atomicAdd(&p.counters[14], (unsigned long long)passS4);
     atomicAdd(&p.counters[15], (unsigned long long)passC);
   }
+}
+
+/* Sum each pixel's samples in the reference's order (main.cpp:430-447) and take the frame's
+ * NaN-skipping maximum (algebra.h:68-91).  HBM-bound: 16 B x spp read + 16 B written per pixel. */
+__global__ void combine_kernel(const float4* __restrict__ samples, float4* __restrict__ fb, uint32_t npix,
+                               uint32_t spp, unsigned int* __restrict__ maxBits) {
+  float m = 0.f;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < npix; px += stride) {
+    V3 acc = mk(0.f, 0.f, 0.f);
+    for (uint32_t k = 0; k < spp; ++k) {
+      const float4 v = samples[(size_t)px * spp + k];
+      acc = vadd(acc, mk(v.x, v.y, v.z));
+    }
+    fb[px] = make_float4(acc.x, acc.y, acc.z, 1.f);
+    if (acc.x > m) m = acc.x;
+    if (acc.y > m) m = acc.y;
+    if (acc.z > m) m = acc.z;
+  }
+  unsigned mb = __reduce_max_sync(0xFFFFFFFFu, __float_as_uint(m));
+  if ((threadIdx.x & 31u) == 0 && mb) atomicMax(maxBits, mb);
 }
 
 /* float4 framebuffer -> packed 12-byte pixels (the reference's `Vec dst[]`, .cl:972) */

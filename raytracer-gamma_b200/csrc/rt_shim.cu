@@ -39,6 +39,7 @@ struct rt_cuda_ctx {
   uint32_t W = 0, H = 0, localRows = 0;
   float4* dFb = nullptr;  size_t fbCap = 0;        /* pixels */
   float* dPacked = nullptr; size_t packedCap = 0;  /* floats */
+  float4* dSamples = nullptr; size_t samplesCap = 0;   /* per-sample results when spp > 1 */
   unsigned char* dRgb8 = nullptr; size_t rgbCap = 0;
   unsigned int* dWork = nullptr;     /* [0] queue head, [1] max bits */
   unsigned long long* dCounters = nullptr;
@@ -132,7 +133,7 @@ extern "C" void rt_cuda_destroy(rt_cuda_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
-  cudaFree(ctx->dScene); cudaFree(ctx->dFb); cudaFree(ctx->dPacked); cudaFree(ctx->dRgb8);
+  cudaFree(ctx->dScene); cudaFree(ctx->dFb); cudaFree(ctx->dPacked); cudaFree(ctx->dRgb8); cudaFree(ctx->dSamples);
   cudaFree(ctx->dWork); cudaFree(ctx->dCounters);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -248,9 +249,28 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   p.counters = ctx->dCounters;
   p.localRows = localRows;
   p.stripRows = stripRows; p.stripFirst = stripFirst; p.stripStride = stripStride;
+  /* work item = one sample of one pixel; samples are summed in order by combine_kernel */
+  const uint32_t spp = (uint32_t)p.cam.nIter * (uint32_t)p.cam.nIter;
+  if (spp == 0) {          /* alias <= 0: the sample loops never run, the frame is black (main.cpp:420) */
+    CU(cudaMemsetAsync(ctx->dFb, 0, pixels * sizeof(float4), ctx->stream));
+    return RT_CUDA_OK;
+  }
   p.tilesX = (width + 7u) / 8u;
   const uint32_t tilesY = (localRows + 3u) / 4u;
-  p.totalWork = p.tilesX * tilesY * 32u;
+  if ((uint64_t)p.tilesX * tilesY * 32u * spp >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
+  p.totalWork = p.tilesX * tilesY * 32u * spp;
+  p.spp = spp;
+  p.samples = nullptr;
+  if (spp > 1) {
+    const size_t need = pixels * spp;
+    if (need > ctx->samplesCap) {
+      CU(cudaStreamSynchronize(ctx->stream));
+      cudaFree(ctx->dSamples); ctx->dSamples = nullptr; ctx->samplesCap = 0;
+      CU(cudaMalloc(&ctx->dSamples, need * sizeof(float4)));
+      ctx->samplesCap = need;
+    }
+    p.samples = ctx->dSamples;
+  }
   p.noFilter = ctx->noFilter;
   p.prefetch = ctx->prefetch;
 
@@ -290,6 +310,11 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
   ctx->launches += 1;
+  if (spp > 1) {
+    combine_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->dSamples, ctx->dFb, (uint32_t)pixels, spp, ctx->dWork + 1);
+    CU(cudaGetLastError());
+    ctx->launches += 1;
+  }
   ctx->stats.grid = grid; ctx->stats.block = RT_BLOCK; ctx->stats.smem_bytes = (uint32_t)smem;
   ctx->stats.staging = (uint32_t)staging;
   return RT_CUDA_OK;

@@ -75,18 +75,24 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
     for (unsigned gx = 0; gx < W; ++gx) {
       Slot s;
       Frame stack[RT_MAX_STACK];
-      memset(&s, 0, sizeof s);
       Counters ctr; memset(&ctr, 0, sizeof ctr);
       float* px = out + ((size_t)k * W + gx) * 3;
-      if (!start_pixel(s, ctr, cam, gx, gy, 0)) { px[0] = px[1] = px[2] = 0.f; continue; }
-      for (;;) {
-        c[6]++; c[7]++;
-        answer(s, sc, ctr, noFilter != 0);
-        if (advance(s, stack, ctr, sc, cam)) {
-          if (finish_sample(s, ctr, cam)) break;
+      V3 samples[64 * 64];
+      int count = 0;
+      for (int si = 0; si < cam.nIter && si < 64; ++si) {
+        for (int sj = 0; sj < cam.nIter && sj < 64; ++sj) {
+          memset(&s, 0, sizeof s);
+          start_task(s, ctr, cam, gx, gy, 0, si, sj);
+          for (;;) {
+            c[6]++; c[7]++;
+            answer(s, sc, ctr, noFilter != 0);
+            if (advance(s, stack, ctr, sc, cam)) break;
+          }
+          samples[count++] = sample_value(s, cam);
         }
       }
-      px[0] = s.acc.x; px[1] = s.acc.y; px[2] = s.acc.z;
+      const V3 acc = combine_samples(samples, count);
+      px[0] = acc.x; px[1] = acc.y; px[2] = acc.z;
       c[0] += ctr.rays; c[1] += ctr.shadow; c[2] += ctr.containQ; c[3] += ctr.containT;
       c[4] += ctr.exactTests; c[5] += ctr.samples;
     }
