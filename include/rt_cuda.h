@@ -64,6 +64,7 @@ typedef struct rt_cuda_stats {
   uint64_t served_trace, served_shadow, served_contain;   /* ... by kind                           */
   uint64_t passes;          /* warp-level passes over the sphere list                               */
   uint64_t passes_trace, passes_shadow2, passes_shadow4, passes_contain;   /* ... by loop variant   */
+  uint64_t phase_cycles[6]; /* -DRT_PHASE_TIMING builds only: warp cycles in refill+vote, set-up, filter loop, resolve, advance */
   uint64_t filter_tests;    /* discriminant filter tests executed = lane_iters * padded sphere count */
   uint64_t null_rays;       /* rays with direction 0 (total internal reflection): certain miss, no sphere loop */
   uint32_t sph_num, sph_padded, lgt_num;

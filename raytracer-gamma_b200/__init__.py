@@ -77,6 +77,7 @@ class Stats(ctypes.Structure):
         ("served_contain", ctypes.c_uint64), ("passes", ctypes.c_uint64),
         ("passes_trace", ctypes.c_uint64), ("passes_shadow2", ctypes.c_uint64),
         ("passes_shadow4", ctypes.c_uint64), ("passes_contain", ctypes.c_uint64),
+        ("phase_cycles", ctypes.c_uint64 * 6),
         ("filter_tests", ctypes.c_uint64), ("null_rays", ctypes.c_uint64),
         ("sph_num", ctypes.c_uint32), ("sph_padded", ctypes.c_uint32), ("lgt_num", ctypes.c_uint32),
         ("width", ctypes.c_uint32), ("height", ctypes.c_uint32), ("local_rows", ctypes.c_uint32),
@@ -87,7 +88,9 @@ class Stats(ctypes.Structure):
     ]
 
     def as_dict(self) -> dict:
-        return {k: getattr(self, k) for k, _ in self._fields_}
+        d = {k: getattr(self, k) for k, _ in self._fields_}
+        d["phase_cycles"] = list(self.phase_cycles)
+        return d
 
 
 # Every symbol include/rt_cuda.h and include/rt_scene.h declare: (name, restype, argtypes)

@@ -234,14 +234,12 @@ enum { K_NULL = 0, K_TRACE = 1, K_SHADOW = 2, K_CONTAIN = 3 };
 /* ---- a pixel in flight --------------------------------------------------------- */
 struct Slot {
   int kind;               /* the pending query */
-  uint32_t pixel;         /* destination index, 0xFFFFFFFF = free slot */
-  int si, sj;             /* sample being traced */
+  uint32_t pixel;         /* index of the sample's result record, 0xFFFFFFFF = free slot */
   int top;                /* frames on the stack = depth of the current call */
   int medium;             /* sphere index of the medium the ray travels in, n = ambient */
   int obj;                /* struck sphere */
   int light;              /* first light of the current shadow batch */
   int ndirs;              /* directions in the pending query (1 for a trace ray) */
-  float pxw, pyw;
   V3 result;              /* "colourSum" of raytracer.h:425 */
   V3 colour, rayD, rayI;  /* the call being evaluated ("currSnapshot") */
   V3 P, Nrm;              /* its hit */
@@ -296,11 +294,10 @@ RT_HD void set_trace_query(Slot& s, Counters& ctr, V3 o, V3 d) {
 RT_HD void start_task(Slot& s, Counters& ctr, const Camera& cam, uint32_t gx, uint32_t gy,
                       uint32_t pixel, int si, int sj) {
   s.pixel = pixel;
-  s.si = si; s.sj = sj;
-  s.pxw = ex_mul(ex_sub((float)gx, ex_mul((float)cam.W, 0.5f)), cam.stepX);
-  s.pyw = ex_mul(ex_sub(ex_mul((float)cam.H, 0.5f), (float)gy), cam.stepY);
-  const float x = ex_mul(ex_add(s.pxw, ex_mul((float)s.sj, cam.aliasStep)), cam.aspect);
-  const float y = ex_add(s.pyw, ex_mul((float)s.si, cam.aliasStep));
+  const float pxw = ex_mul(ex_sub((float)gx, ex_mul((float)cam.W, 0.5f)), cam.stepX);
+  const float pyw = ex_mul(ex_sub(ex_mul((float)cam.H, 0.5f), (float)gy), cam.stepY);
+  const float x = ex_mul(ex_add(pxw, ex_mul((float)sj, cam.aliasStep)), cam.aspect);
+  const float y = ex_add(pyw, ex_mul((float)si, cam.aliasStep));
   const V3 d = vunit(mk(x, y, cam.zoom));
   s.rayD = d; s.rayI = mk(1.f, 1.f, 1.f); s.colour = mk(0.f, 0.f, 0.f);
   s.result = mk(0.f, 0.f, 0.f);

@@ -36,7 +36,7 @@ namespace rtg {
 #define RT_BLOCK 256
 #define RT_LIST_MAX 24
 #define RT_CONST_MAX_SPHERES 1024
-#define RT_NUM_COUNTERS 16
+#define RT_NUM_COUNTERS 24
 #define RT_NO_PIXEL 0xFFFFFFFFu
 
 struct TraceParams {
@@ -113,6 +113,10 @@ __device__ __forceinline__ bool work_to_task(const TraceParams& p, uint32_t idx,
 
 /* Per-warp state shared by the passes. */
 struct WarpCtx {
+#ifdef RT_PHASE_TIMING
+  long long t0;
+  long long phase[6];       /* refill+vote, set-up, filter loop, resolve, advance, (spare) */
+#endif
   const float4* filt;       /* filter records (shared memory, or unused with __constant__) */
   unsigned short* list;     /* per-lane candidate lists: list[k * RT_BLOCK + tid]          */
   uint32_t tid;
@@ -193,6 +197,14 @@ __device__ __forceinline__ void gather(const WarpCtx& w, unsigned comb, uint32_t
 
 #define RT_FULL 0xFFFFFFFFu
 
+/* Optional phase timing (development builds, -DRT_PHASE_TIMING): wall cycles a warp spends in
+ * each phase of a pass, accumulated into counters[16..21]. */
+#ifdef RT_PHASE_TIMING
+#define RT_TICK(slot) do { const long long now_ = clock64(); w.phase[slot] += now_ - w.t0; w.t0 = now_; } while (0)
+#else
+#define RT_TICK(slot) do { } while (0)
+#endif
+
 /* Cold path (list overflow, non-finite geometry, no_filter debug mode): answer the slot's
  * pending query with the exact test against every sphere.  Out of line; returns the
  * number of exact tests. */
@@ -228,7 +240,7 @@ __device__ __noinline__ uint32_t exact_all(const SceneView sc, Slot* s, unsigned
 
 /* ---- trace pass: up to two rays per lane ---------------------------------------- */
 template <bool USE_CONST>
-__device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                            int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_T;
   static_assert(G <= 16, "two 16-bit mask fields");
@@ -252,6 +264,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& 
   const Dir2 DD = pack_dir(D0, D1);
   int cnt = 0;
   bool overflow = false;
+  RT_TICK(1);
   if (!p.noFilter) {
     const uint32_t groups = w.nPad / G;
     for (uint32_t g = 0; g < groups; ++g) {
@@ -275,6 +288,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& 
   float t0 = 1000.f, t1 = 1000.f;
   int h0 = -1, h1 = -1;
   const int maxc = __reduce_max_sync(RT_FULL, cnt);
+  RT_TICK(2);
 #pragma unroll 1
   for (int k = 0; k < maxc; ++k) {
     if (k < cnt && !overflow) {
@@ -302,7 +316,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, const WarpCtx& 
  * A lane with no shadow batch waiting may bring a TRACE slot instead: a trace ray is the
  * same query with one direction, so it rides along for free and keeps the lane busy. */
 template <bool USE_CONST, int ND>
-__device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                             Counters& ctr) {
   constexpr int G = RT_GROUP_S;
   static_assert(G * ND <= 32, "ND mask fields of G bits");
@@ -334,6 +348,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
   for (int k = 0; k < ND / 2; ++k) DP[k] = pack_dir(D[2 * k], D[2 * k + 1]);
   int cnt = 0;
   bool overflow = false;
+  RT_TICK(1);
   if (!p.noFilter) {
     const uint32_t groups = w.nPad / G;
     for (uint32_t g = 0; g < groups; ++g) {
@@ -364,6 +379,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
   float t0 = 1000.f;
   int h0 = -1;
   const int maxc = __reduce_max_sync(RT_FULL, cnt);
+  RT_TICK(2);
 #pragma unroll 1
   for (int k = 0; k < maxc; ++k) {
     if (k < cnt && !overflow) {
@@ -395,7 +411,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const WarpCtx&
 
 /* ---- containment pass: up to two probe points per lane ---------------------------- */
 template <bool USE_CONST>
-__device__ __forceinline__ void pass_contain(const TraceParams& p, const WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_contain(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                              int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_C;
   static_assert(G <= 16, "two 16-bit mask fields");
@@ -408,6 +424,7 @@ __device__ __forceinline__ void pass_contain(const TraceParams& p, const WarpCtx
   const Origin2 OO = pack_origin(O0, O1);
   int cnt = 0;
   bool overflow = false;
+  RT_TICK(1);
   if (!p.noFilter) {
     const uint32_t groups = w.nPad / G;
     for (uint32_t g = 0; g < groups; ++g) {
@@ -428,6 +445,7 @@ __device__ __forceinline__ void pass_contain(const TraceParams& p, const WarpCtx
   }
   int h0 = -1, h1 = -1;
   const int maxc = __reduce_max_sync(RT_FULL, cnt);
+  RT_TICK(2);
 #pragma unroll 1
   for (int k = 0; k < maxc; ++k) {
     if (k < cnt && !overflow) {
@@ -522,6 +540,10 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
   w.list = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
   w.tid = tid;
   w.nPad = p.sc.nPad;
+#ifdef RT_PHASE_TIMING
+  w.t0 = clock64();
+  for (int i = 0; i < 6; ++i) w.phase[i] = 0;
+#endif
 
   Slot slots[NSLOTS];
   Frame stacks[NSLOTS * RT_MAX_STACK];
@@ -614,6 +636,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
       pass_contain<USE_CONST>(p, w, slots, c0, c1, ctr);
       passC++; servedC += (unsigned)((c0 >= 0) + (c1 >= 0));
     }
+    RT_TICK(3);
     /* ---- advance the served slots (one code instance, same kind across the warp) ---- */
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
@@ -623,8 +646,13 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
         tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
       }
     }
+    RT_TICK(4);
   }
 
+#ifdef RT_PHASE_TIMING
+  if (lane == 0)
+    for (int i = 0; i < 6; ++i) atomicAdd(&p.counters[16 + i], (unsigned long long)w.phase[i]);
+#endif
   /* ---- per-warp reductions ---- */
   unsigned mb = __float_as_uint(laneMax);   /* laneMax >= 0: uint order == float order */
   mb = __reduce_max_sync(RT_FULL, mb);

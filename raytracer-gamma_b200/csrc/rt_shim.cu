@@ -438,6 +438,7 @@ extern "C" int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out) {
   s.active_lane_iters = c[7] + c[8] + c[9];     /* sub-queries actually served (trace/shadow/contain) */
   s.served_trace = c[7]; s.served_shadow = c[8]; s.served_contain = c[9]; s.passes = c[11];
   s.passes_trace = c[12]; s.passes_shadow2 = c[13]; s.passes_shadow4 = c[14]; s.passes_contain = c[15];
+  for (int i = 0; i < 6; ++i) s.phase_cycles[i] = c[16 + i];
   s.filter_tests = ctx->noFilter ? 0 : c[10] * (unsigned long long)ctx->nPad;
   s.sph_num = ctx->n; s.sph_padded = ctx->nPad; s.lgt_num = ctx->nl;
   s.width = ctx->W; s.height = ctx->H; s.local_rows = ctx->localRows;

@@ -9,15 +9,13 @@ print(pkg.device_info(0))
 r = pkg.Renderer(0)
 print("ffma_peak TFLOP/s:", [round(r.ffma_peak(8192), 2) for _ in range(3)])
 cases = [
-    ("default 1080p a1 s4", pkg.default_scene(), 1920, 1080, 1.0, 4, {}),
-    ("synth256 4K a1 s6 mb3", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 3}),
-    ("synth256 4K a1 s6 mb2", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"min_blocks": 2}),
-    ("synth1024 4K a1 s8 mb2", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 2}),
-    ("synth1024 4K a1 s8 mb3", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3}),
-    ("synth1024 4K a1 s8 mb3 slots4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "slots": 4}),
-    ("synth1024 4K a1 s8 mb2 slots4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 2, "slots": 4}),
-    ("synth1024 4K a1 s8 mb3 slots2", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "slots": 2}),
-    ("synth4096 2K a1 s8 mb3", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {"min_blocks": 3}),
+    ("synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {}),
+    ("synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {}),
+    ("synth1024 4K a1 s8 mb4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4}),
+    ("synth1024 4K a1 s8 mb4 slots2", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4, "slots": 2}),
+    ("synth1024 4K a1 s8 mb3 slots3", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "slots": 3}),
+    ("synth1024 4K a1 s8 1blk", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"blocks_per_sm": 1}),
+    ("synth1024 4K a1 s8 slots2", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"slots": 2}),
 ]
 if len(sys.argv) > 1:
     cases = [c for c in cases if any(a in c[0] for a in sys.argv[1:])]
@@ -46,4 +44,5 @@ for name, (sph, lgt), W, H, alias, S, opts in cases:
         "served_T/S/C": [st["served_trace"], st["served_shadow"], st["served_contain"]],
         "passes_T/S2/S4/C": [st["passes_trace"], st["passes_shadow2"], st["passes_shadow4"], st["passes_contain"]],
         "exact_per_query": round(st["exact_tests"] / max(1, st["active_lane_iters"]), 3),
+        "phase_pct(refill+vote,setup,loop,resolve,advance)": [round(100.0 * c / max(1, sum(st["phase_cycles"])), 1) for c in st["phase_cycles"][:5]],
         "rays": st["rays"], "grid": st["grid"], "smem": st["smem_bytes"], "staging": st["staging"]}))
