@@ -52,6 +52,9 @@ RT_HD float ex_sub(float a, float b) { return __fadd_rn(a, -b); }
 RT_HD float ex_mul(float a, float b) { return __fmul_rn(a, b); }
 RT_HD_NI float ex_div(float a, float b) { return __fdiv_rn(a, b); }
 RT_HD_NI float ex_sqrt(float a) { return __fsqrt_rn(a); }
+/* inline twins for the few hot spots where independent divisions / roots should overlap */
+RT_HD float ex_div_i(float a, float b) { return __fdiv_rn(a, b); }
+RT_HD float ex_sqrt_i(float a) { return __fsqrt_rn(a); }
 RT_HD double exd_add(double a, double b) { return __dadd_rn(a, b); }
 RT_HD double exd_sub(double a, double b) { return __dadd_rn(a, -b); }
 RT_HD double exd_mul(double a, double b) { return __dmul_rn(a, b); }
@@ -65,6 +68,8 @@ RT_HD float ex_sub(float a, float b) { return a - b; }
 RT_HD float ex_mul(float a, float b) { return a * b; }
 RT_HD float ex_div(float a, float b) { return a / b; }
 RT_HD float ex_sqrt(float a) { return sqrtf(a); }
+RT_HD float ex_div_i(float a, float b) { return a / b; }
+RT_HD float ex_sqrt_i(float a) { return sqrtf(a); }
 RT_HD double exd_add(double a, double b) { return a + b; }
 RT_HD double exd_sub(double a, double b) { return a - b; }
 RT_HD double exd_mul(double a, double b) { return a * b; }
@@ -84,6 +89,7 @@ RT_HD float vdot(V3 a, V3 b) {
   return ex_add(ex_add(ex_mul(a.x, b.x), ex_mul(a.y, b.y)), ex_mul(a.z, b.z));
 }
 RT_HD V3 vunit(V3 v) { float l = ex_div(1.f, ex_sqrt(vdot(v, v))); return vscale(l, v); }
+RT_HD V3 vunit_i(V3 v) { float l = ex_div_i(1.f, ex_sqrt_i(vdot(v, v))); return vscale(l, v); }
 /* raytracer.h:235-241 (NaN is not significant) */
 RT_HD bool significant(V3 c) { return (c.x >= 0.001f) || (c.y >= 0.001f) || (c.z >= 0.001f); }
 
@@ -244,10 +250,10 @@ struct Slot {
   V3 colour, rayD, rayI;  /* the call being evaluated ("currSnapshot") */
   V3 P, Nrm;              /* its hit */
   V3 lit;                 /* matte accumulation, raytracer.h:325 */
-  /* geometry of the pending query */
-  V3 qo;                  /* ray origin / probe point */
-  V3 qd[RT_SHADOW_BATCH]; /* direction(s): qd[0] for a trace ray, one per light for a shadow batch */
-  float gap[RT_SHADOW_BATCH];   /* squared distance to the light, raytracer.h:280 */
+  /* geometry of the pending query: a trace ray is (qo, rayD); a containment probe is the
+   * point qo; a shadow batch starts at P towards lights light..light+ndirs-1 — its
+   * directions live only for the pass that serves it (ShadowGeo), not in the record */
+  V3 qo;
   /* answer, filled by the sphere pass */
   float minT; int hitIdx; /* closest hit (trace) / first container (probe) */
   uint32_t blocked;       /* shadow batch: bit k = light `light+k` is occluded */
@@ -278,10 +284,11 @@ RT_HD Camera make_camera(uint32_t W, uint32_t H, float zoom, float alias, int S,
   return c;
 }
 
+/* The caller has already made `d` the current call's direction (s.rayD). */
 RT_HD void set_trace_query(Slot& s, Counters& ctr, V3 o, V3 d) {
   s.kind = K_TRACE;
   s.ndirs = 1;
-  s.qo = o; s.qd[0] = d;
+  s.qo = o;
   s.minT = 1000.f; s.hitIdx = -1;
   if (vdot(d, d) == 0.f) ctr.nullRays++;   /* zero direction: certain miss (see make_dir) */
 }
@@ -318,20 +325,30 @@ RT_HD V3 combine_samples(const V3* samples, int count) {
   return acc;
 }
 
-/* raytracer.h:272-286 for the lights light .. light+ndirs-1: shadow rays from P */
+/* Next shadow batch of the current hit: lights light .. light+ndirs-1. */
 RT_HD void setup_shadow_batch(Slot& s, const SceneView& sc) {
   int nb = (int)sc.nl - s.light;
   if (nb > RT_SHADOW_BATCH) nb = RT_SHADOW_BATCH;
   s.kind = K_SHADOW;
   s.ndirs = nb;
-  s.qo = s.P;
   s.blocked = 0u;
+}
+
+/* The rays of a shadow batch (raytracer.h:279-286): from P towards each light, with the
+ * squared distance to it.  Rebuilt by the pass that serves the batch. */
+struct ShadowGeo { V3 d[RT_SHADOW_BATCH]; float gap[RT_SHADOW_BATCH]; };
+RT_HD void shadow_geo(const Slot& s, const SceneView& sc, ShadowGeo& g) {
+#ifdef __CUDACC__
+#pragma unroll
+#endif
   for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
-    if (k < nb) {
+    if (k < s.ndirs) {
       const float4_ lp = sc.lpos[s.light + k];
       const V3 dir = vsub(mk(lp.x, lp.y, lp.z), s.P);
-      s.gap[k] = vdot(dir, dir);
-      s.qd[k] = vunit(dir);
+      g.gap[k] = vdot(dir, dir);
+      g.d[k] = vunit_i(dir);       /* independent normalisations: inline so they overlap */
+    } else {
+      g.gap[k] = 0.f; g.d[k] = mk(0.f, 0.f, 0.f);
     }
   }
 }
@@ -494,7 +511,8 @@ RT_HD int after_matte(Slot& s, Counters& ctr, const SceneView& sc, bool haveMatt
 /* Advance the slot after its query has been answered (hitIdx/minT or blocked).
  * Returns true when the slot's current SAMPLE is finished (result valid);
  * otherwise the slot holds its next query. */
-RT_HD bool advance(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, const Camera& cam) {
+RT_HD bool advance(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, const Camera& cam,
+                   const ShadowGeo* sg) {
   int act;
   if (s.kind == K_TRACE) {
     ctr.rays++;
@@ -508,7 +526,7 @@ RT_HD bool advance(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, co
       /* raytracer.h:171-181 for the winning sphere */
       const float4_ g = sc.geo[s.hitIdx];
       s.obj = s.hitIdx;
-      s.P = vadd(s.qo, vscale(s.minT, s.qd[0]));
+      s.P = vadd(s.qo, vscale(s.minT, s.rayD));
       s.Nrm = vunit(vsub(s.P, mk(g.x, g.y, g.z)));
       const float opacity = sc.matA[s.obj].w;
       if (opacity > 0.f) {
@@ -521,15 +539,18 @@ RT_HD bool advance(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, co
     }
   } else if (s.kind == K_SHADOW) {
     /* raytracer.h:328-363 for the lights of this batch, in index order */
+#ifdef __CUDACC__
+#pragma unroll
+#endif
     for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
       if (k < s.ndirs) {
         ctr.rays++; ctr.shadow++;
         if (!((s.blocked >> k) & 1u)) {
           const float4_ lp = sc.lpos[s.light + k], lc = sc.lcol[s.light + k];
           const V3 dist = vsub(mk(lp.x, lp.y, lp.z), s.P);
-          const float incidence = vdot(s.Nrm, s.qd[k]);   /* qd[k] = the vector calculateMatte rebuilds */
+          const float incidence = vdot(s.Nrm, sg->d[k]);   /* d[k] = the vector calculateMatte rebuilds */
           if (incidence > 0.f) {
-            const float kk = ex_div(incidence, vdot(dist, dist));
+            const float kk = ex_div_i(incidence, vdot(dist, dist));
             s.lit = vadd(s.lit, vscale(kk, mk(lc.x, lc.y, lc.z)));
           }
         }

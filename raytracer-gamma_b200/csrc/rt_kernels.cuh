@@ -119,6 +119,7 @@ struct WarpCtx {
 #endif
   const float4* filt;       /* filter records (shared memory, or unused with __constant__) */
   unsigned short* list;     /* per-lane candidate lists: list[k * RT_BLOCK + tid]          */
+  float* geo;               /* per-lane shadow-batch rays of the current pass: geo[w * RT_BLOCK + tid], 16 words */
   uint32_t tid;
   uint32_t nPad;
 };
@@ -213,19 +214,21 @@ __device__ __noinline__ uint32_t exact_all(const SceneView sc, Slot* s, unsigned
   if (s->kind == K_TRACE) {
     float t = 1000.f; int h = -1;
     DirQ D;
-    if (make_dir(D, s->qo, s->qd[0])) {
-      for (uint32_t i = 0; i < sc.n; ++i) resolve_trace(t, h, s->qo, s->qd[0], sc.geo[i], i);
+    if (make_dir(D, s->qo, s->rayD)) {
+      for (uint32_t i = 0; i < sc.n; ++i) resolve_trace(t, h, s->qo, s->rayD, sc.geo[i], i);
       tests = sc.n;
     }
     s->minT = t; s->hitIdx = h;
   } else if (s->kind == K_SHADOW) {
     unsigned blocked = s->blocked;
+    ShadowGeo sg;
+    shadow_geo(*s, sc, sg);
     for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
       if ((subs >> k) & 1u) {
         blocked &= ~(1u << k);
         for (uint32_t i = 0; i < sc.n; ++i) {
           ++tests;
-          if (resolve_shadow(s->qo, s->qd[k], s->gap[k], sc.geo[i])) { blocked |= 1u << k; break; }
+          if (resolve_shadow(s->P, sg.d[k], sg.gap[k], sc.geo[i])) { blocked |= 1u << k; break; }
         }
       }
     }
@@ -250,12 +253,12 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slo
   bool live0 = false, live1 = false, exact0 = false, exact1 = false;
   if (s0 >= 0) {
     O0 = make_origin(slots[s0].qo);
-    live0 = make_dir(D0, slots[s0].qo, slots[s0].qd[0]);
+    live0 = make_dir(D0, slots[s0].qo, slots[s0].rayD);
     exact0 = live0 && (p.noFilter || !(origin_filterable(O0) && dir_filterable(D0)));
   }
   if (s1 >= 0) {
     O1 = make_origin(slots[s1].qo);
-    live1 = make_dir(D1, slots[s1].qo, slots[s1].qd[0]);
+    live1 = make_dir(D1, slots[s1].qo, slots[s1].rayD);
     exact1 = live1 && (p.noFilter || !(origin_filterable(O1) && dir_filterable(D1)));
   }
   const unsigned fld = (1u << G) - 1u;
@@ -297,7 +300,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slo
       if (i < p.sc.n) {
         ctr.exactTests++;
         const Slot& q = slots[sub ? s1 : s0];
-        const float t = ray_sphere_t(p.sc.geo[i], q.qo, q.qd[0]);
+        const float t = ray_sphere_t(p.sc.geo[i], q.qo, q.rayD);
         if (t > 0.f) {       /* raytracer.h:166-188; strict <: first index wins ties */
           if (sub) { if (t < t1) { t1 = t; h1 = (int)i; } }
           else     { if (t < t0) { t0 = t; h0 = (int)i; } }
@@ -327,13 +330,33 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Sl
 #pragma unroll
   for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; }
   if (s0 >= 0) {
-    O = make_origin(slots[s0].qo);
+    /* the batch's rays (or the rider's single ray) go to the lane's shared-memory scratch:
+     * resolve and advance read them back, the slot record does not carry them */
     asTrace = slots[s0].kind == K_TRACE;
+    ShadowGeo g;
+    V3 org;
+    if (asTrace) {
+      org = slots[s0].qo;
+      g.d[0] = slots[s0].rayD; g.gap[0] = 0.f;
+#pragma unroll
+      for (int k = 1; k < RT_SHADOW_BATCH; ++k) { g.d[k] = mk(0.f, 0.f, 0.f); g.gap[k] = 0.f; }
+    } else {
+      org = slots[s0].P;
+      shadow_geo(slots[s0], p.sc, g);
+    }
+#pragma unroll
+    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+      w.geo[(4 * k + 0) * RT_BLOCK + w.tid] = g.d[k].x;
+      w.geo[(4 * k + 1) * RT_BLOCK + w.tid] = g.d[k].y;
+      w.geo[(4 * k + 2) * RT_BLOCK + w.tid] = g.d[k].z;
+      w.geo[(4 * k + 3) * RT_BLOCK + w.tid] = g.gap[k];
+    }
+    O = make_origin(org);
     const bool ofil = origin_filterable(O);
     const int nd = slots[s0].ndirs;
 #pragma unroll
     for (int k = 0; k < ND; ++k) {
-      if (k < nd && make_dir(D[k], slots[s0].qo, slots[s0].qd[k])) {
+      if (k < nd && make_dir(D[k], org, g.d[k])) {
         live |= 1u << k;
         if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
       }
@@ -387,15 +410,16 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Sl
       const uint32_t i = e & 0x3FFFu, sub = e >> 14;
       if (i < p.sc.n && !((blocked >> sub) & 1u)) {
         ctr.exactTests++;
-        const Slot& q = slots[s0];
-        const V3 d = q.qd[sub];
-        const float t = ray_sphere_t(p.sc.geo[i], q.qo, d);
+        const V3 d = mk(w.geo[(4 * sub + 0) * RT_BLOCK + w.tid], w.geo[(4 * sub + 1) * RT_BLOCK + w.tid],
+                        w.geo[(4 * sub + 2) * RT_BLOCK + w.tid]);
+        const V3 org = asTrace ? slots[s0].qo : slots[s0].P;
+        const float t = ray_sphere_t(p.sc.geo[i], org, d);
         if (t > 0.f) {
           if (asTrace) {          /* closest hit, raytracer.h:166-188 */
             if (t < t0) { t0 = t; h0 = (int)i; }
           } else if (t < 1000.f) { /* occluder iff |t d|^2 < gap, raytracer.h:291-304 (see resolve_shadow) */
             const V3 dist = vscale(t, d);
-            if (vdot(dist, dist) < q.gap[sub]) blocked |= 1u << sub;
+            if (vdot(dist, dist) < w.geo[(4 * sub + 3) * RT_BLOCK + w.tid]) blocked |= 1u << sub;
           }
         }
       }
@@ -485,9 +509,9 @@ __device__ __forceinline__ void prefetch_slot(const Slot& s) {
  * load/store chain through L2) and written back once.  Returns the slot's new
  * (kind | ndirs << 4) tag for the lane's register-resident census. */
 __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, Slot* slot, Frame* stack, Counters& ctr,
-                                                 float& laneMax) {
+                                                 float& laneMax, const ShadowGeo* sg) {
   Slot s = *slot;
-  if (advance(s, stack, ctr, p.sc, p.cam)) {
+  if (advance(s, stack, ctr, p.sc, p.cam, sg)) {
     const V3 v = sample_value(s, p.cam);
     if (p.spp == 1u) {
       /* one sample per pixel: the pixel is 0 + sample (main.cpp:420,446) */
@@ -510,7 +534,7 @@ __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, Slot* slo
 template <bool USE_CONST, int MIN_BLOCKS, int NSLOTS>
 __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const TraceParams p) {
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists] */
+  /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists][shadow-ray scratch] */
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float4* sFilt = reinterpret_cast<float4*>(smem_raw + 16);
   const uint32_t filtBytes = USE_CONST ? 0u : p.sc.nPad * 16u;
@@ -538,6 +562,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
   WarpCtx w;
   w.filt = sFilt;
   w.list = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
+  w.geo = reinterpret_cast<float*>(smem_raw + 16 + filtBytes + RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short));
   w.tid = tid;
   w.nPad = p.sc.nPad;
 #ifdef RT_PHASE_TIMING
@@ -638,11 +663,20 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
     }
     RT_TICK(3);
     /* ---- advance the served slots (one code instance, same kind across the warp) ---- */
+    ShadowGeo sg;
+    if (mode == K_SHADOW && sv0 >= 0) {       /* the rays of the batch just served */
+#pragma unroll
+      for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+        sg.d[k] = mk(w.geo[(4 * k + 0) * RT_BLOCK + tid], w.geo[(4 * k + 1) * RT_BLOCK + tid],
+                     w.geo[(4 * k + 2) * RT_BLOCK + tid]);
+        sg.gap[k] = w.geo[(4 * k + 3) * RT_BLOCK + tid];
+      }
+    }
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
       const int sv = r ? sv1 : sv0;
       if (sv >= 0) {
-        const uint32_t tg = advance_slot(p, &slots[sv], &stacks[sv * RT_MAX_STACK], ctr, laneMax);
+        const uint32_t tg = advance_slot(p, &slots[sv], &stacks[sv * RT_MAX_STACK], ctr, laneMax, &sg);
         tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
       }
     }

@@ -279,7 +279,8 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if (staging == 0) staging = (ctx->n > 0 && ctx->nPad <= 64) ? 1 : 2;
   if (staging == 1 && (ctx->n == 0 || ctx->nPad > RT_CONST_MAX_SPHERES)) staging = 2;
   const bool useConst = (staging == 1);
-  const size_t smem = 16 + (useConst ? 0 : (size_t)ctx->nPad * 16) + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short);
+  const size_t smem = 16 + (useConst ? 0 : (size_t)ctx->nPad * 16) + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
+                      + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
   /* variants: MIN_BLOCKS resident CTAs per SM (register budget), NSLOTS pixels in flight per lane */
   const int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
   const int nslots = ctx->slots ? ctx->slots : RT_DEFAULT_SLOTS;

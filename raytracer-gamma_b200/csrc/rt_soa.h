@@ -5,6 +5,7 @@
 #define RT_SOA_H
 
 #include <math.h>
+#include <cmath>
 #include <vector>
 #include "rt_types.h"
 #include "rt_core.cuh"
@@ -64,7 +65,12 @@ static inline void build_scene_soa(const rt_sphere* spheres, uint32_t n, const r
       const double cc = cx * cx + cy * cy + cz * cz, rr = r * r;
       /* see "Filter" in rt_core.cuh: certain-miss threshold with all rounding slack folded in */
       const double w = (cc - rr) - kappa * (cc + rr) - 2.5e-6 * fabs(r) - 1e-11;
-      filt[i] = float4_{s.pos.x, s.pos.y, s.pos.z, float_round_down(w)};
+      const float wf = float_round_down(w);
+      const bool finite = std::isfinite(s.pos.x) && std::isfinite(s.pos.y) && std::isfinite(s.pos.z) &&
+                          std::isfinite(s.radius) && std::isfinite(wf);
+      /* geometry the filter cannot represent is ALWAYS a candidate (w = -inf, finite products):
+       * it then goes through the reference's exact expressions for every query */
+      filt[i] = finite ? float4_{s.pos.x, s.pos.y, s.pos.z, wf} : float4_{0.f, 0.f, 0.f, -INFINITY};
       geo[i] = float4_{s.pos.x, s.pos.y, s.pos.z, s.radius};
       matA[i] = float4_{s.material.matteColour.x, s.material.matteColour.y,
                         s.material.matteColour.z, s.material.opacity};

@@ -16,32 +16,34 @@
 using namespace rtg;
 
 /* Answer the slot's pending query the way one pass of the kernel does. */
-static void answer(Slot& s, const SceneView& sc, Counters& ctr, bool noFilter) {
-  const OriginQ O = make_origin(s.qo);
+static void answer(Slot& s, const SceneView& sc, Counters& ctr, bool noFilter, ShadowGeo& sg) {
+  const V3 org = (s.kind == K_SHADOW) ? s.P : s.qo;
+  const OriginQ O = make_origin(org);
   const bool ofil = origin_filterable(O);
   if (s.kind == K_TRACE) {
     DirQ D;
     s.minT = 1000.f; s.hitIdx = -1;
-    if (!make_dir(D, s.qo, s.qd[0])) return;           /* zero direction: certain miss */
+    if (!make_dir(D, s.qo, s.rayD)) return;           /* zero direction: certain miss */
     const bool fil = !noFilter && ofil && dir_filterable(D);
     for (uint32_t i = 0; i < (fil ? sc.nPad : sc.n); ++i) {
       if (fil && filter_ray(O, D, filter_ch(O, sc.filt[i]), sc.filt[i]) < 0.f) continue;
       if (i >= sc.n) continue;
       ctr.exactTests++;
-      resolve_trace(s.minT, s.hitIdx, s.qo, s.qd[0], sc.geo[i], i);
+      resolve_trace(s.minT, s.hitIdx, s.qo, s.rayD, sc.geo[i], i);
     }
   } else if (s.kind == K_SHADOW) {
     s.blocked = 0u;
+    shadow_geo(s, sc, sg);
     for (int k = 0; k < s.ndirs; ++k) {
       DirQ D;
-      if (!make_dir(D, s.qo, s.qd[k])) continue;
+      if (!make_dir(D, org, sg.d[k])) continue;
       const bool fil = !noFilter && ofil && dir_filterable(D);
       for (uint32_t i = 0; i < (fil ? sc.nPad : sc.n); ++i) {
         if (fil && filter_ray(O, D, filter_ch(O, sc.filt[i]), sc.filt[i]) < 0.f) continue;
         if (i >= sc.n) continue;
         if ((s.blocked >> k) & 1u) break;
         ctr.exactTests++;
-        if (resolve_shadow(s.qo, s.qd[k], s.gap[k], sc.geo[i])) s.blocked |= 1u << k;
+        if (resolve_shadow(org, sg.d[k], sg.gap[k], sc.geo[i])) s.blocked |= 1u << k;
       }
     }
   } else if (s.kind == K_CONTAIN) {
@@ -85,8 +87,9 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
           start_task(s, ctr, cam, gx, gy, 0, si, sj);
           for (;;) {
             c[6]++; c[7]++;
-            answer(s, sc, ctr, noFilter != 0);
-            if (advance(s, stack, ctr, sc, cam)) break;
+            ShadowGeo sg;
+            answer(s, sc, ctr, noFilter != 0, sg);
+            if (advance(s, stack, ctr, sc, cam, &sg)) break;
           }
           samples[count++] = sample_value(s, cam);
         }

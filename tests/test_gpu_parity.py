@@ -154,6 +154,22 @@ def test_edge_cases(pkg, orc_mod, oracle, gpu):
     fresh.close()
 
 
+def test_rare_paths(pkg, orc_mod, oracle, gpu):
+    """> 4 lights (several shadow batches), candidate-list overflow, non-finite filter records,
+    the largest scene the library accepts."""
+    from test_hostsim import _stress_scenes
+    for name, (sph, lgt) in _stress_scenes(pkg).items():
+        fb, mx, st = _render(gpu, sph, lgt, 96, 64, -4.0, 1.0, 8)
+        ref, ctr = oracle.render(sph, lgt, 96, 64, -4.0, 1.0, 8)
+        _assert_parity(orc_mod, oracle, ref, fb)
+        assert st["rays"] == ctr["rays"] and st["shadow_rays"] == ctr["shadow_rays"], name
+    sph, lgt = pkg.synth_scene(12288, 4, seed=2)          # RT_CUDA_MAX_SPHERES
+    fb, mx, st = _render(gpu, sph, lgt, 48, 27, -4.0, 1.0, 8)
+    ref, ctr = oracle.render(sph, lgt, 48, 27, -4.0, 1.0, 8)
+    _assert_parity(orc_mod, oracle, ref, fb)
+    assert st["rays"] == ctr["rays"]
+
+
 def test_strips_reassemble_to_the_full_frame(pkg, orc_mod, gpu):
     """Row-strip shards (the multi-GPU partition) tile the 1-GPU frame byte for byte,
     and the max over shards is the frame's max."""

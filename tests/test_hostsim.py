@@ -85,3 +85,39 @@ def test_machine_edge_cases(pkg, orc_mod, oracle, hostsim):
     a, _ = oracle.render(inside, lgt, 48, 36, -4.0, 1.0, 6)
     b, _ = hostsim(inside, lgt, 48, 36, -4.0, 1.0, 6)
     assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b))
+
+
+def _stress_scenes(pkg):
+    """Scenes that push the kernel's rare paths: > 4 lights (several shadow batches per hit),
+    many spheres pierced by one ray (candidate-list overflow -> exact fallback), huge
+    coordinates (filter values overflow -> non-filterable geometry -> exact fallback)."""
+    out = {}
+    sph, lgt = pkg.synth_scene(48, 4, seed=21)
+    six = np.zeros(6, pkg.LIGHT_DTYPE)
+    six[:4] = lgt
+    six[4]["pos"], six[4]["col"] = (5, 90, 30), (0.4, 0.2, 0.6)
+    six[5]["pos"], six[5]["col"] = (-60, -40, 10), (0.3, 0.3, 0.1)
+    out["six_lights"] = (sph, six)
+    # 40 thin transparent shells stacked along the view axis
+    shells = np.zeros(40, pkg.SPHERE_DTYPE)
+    for i in range(40):
+        shells[i]["pos"] = (0.05 * i, 0.0, -8.0 - 0.01 * i)
+        shells[i]["radius"] = 2.0 + 0.05 * i
+        shells[i]["matte"] = (0.3, 0.5, 0.7)
+        shells[i]["gloss"] = (0.1, 0.1, 0.1)
+        shells[i]["opacity"] = 0.35
+        shells[i]["refractiveIndex"] = 1.0 + 0.01 * i
+    out["shells"] = (shells, lgt[:2])
+    far = sph.copy()
+    far["pos"][5] = (3e19, 1e19, -2e19)       # |c|^2 overflows float: its filter record is not finite
+    far["radius"][5] = 1e19
+    out["huge_sphere"] = (far, lgt)
+    return out
+
+
+def test_machine_rare_paths(pkg, orc_mod, oracle, hostsim):
+    for name, (sph, lgt) in _stress_scenes(pkg).items():
+        a, ca = oracle.render(sph, lgt, 64, 48, -4.0, 1.0, 8)
+        b, cb = hostsim(sph, lgt, 64, 48, -4.0, 1.0, 8)
+        assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), name
+        assert ca["rays"] == cb["rays"] and ca["shadow_rays"] == cb["shadow_rays"], name
