@@ -208,3 +208,17 @@ def test_full_size_properties_config3(pkg, orc_mod, oracle, gpu):
     # quantised image: bytes equal the reference quantiser applied to the float image
     rgb = gpu.readback_rgb8()
     assert np.array_equal(rgb[rows[0]::rows[2]][:rows[1]], oracle.quantise(got, mx))
+
+
+def test_host_program_writes_the_reference_ppm(pkg, tmp_path):
+    """raytracer-gamma_b200/host/main.cpp (the reference's main() over the C-ABI) renders the
+    default frame; the PPM it writes has the md5 of the reference CPU render's PPM."""
+    import subprocess
+    assert pkg.HOST_BIN.exists(), "rt_gamma was not built"
+    out = tmp_path / "testPPM.ppm"
+    res = subprocess.run([str(pkg.HOST_BIN), "--out", str(out)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert "Exec time" in res.stdout
+    assert hashlib.md5(out.read_bytes()).hexdigest() == FACTS["default_800x600_a3_s6"]["ppm_md5"]
+    res = subprocess.run([str(pkg.HOST_BIN), "--list"], capture_output=True, text=True, timeout=60)
+    assert res.returncode == 0 and "CUDA device" in res.stdout
