@@ -35,6 +35,20 @@ void rt_scene_default(rt_sphere spheres[RT_SCENE_DEFAULT_SPHERES],
 int rt_scene_synth(unsigned sphNum, unsigned lgtNum, uint64_t seed,
                    rt_sphere* spheres, rt_light* lights);
 
+/* Scene files (the reference has none: its scene is a literal in main()).  A text file,
+ * one record per line, floats written as C99 hex-floats so a save/load round trip is exact:
+ *     rtgamma-scene 1
+ *     sphere  cx cy cz radius  matte.r matte.g matte.b  gloss.r gloss.g gloss.b  opacity refractiveIndex
+ *     light   px py pz  col.r col.g col.b
+ * Material fields are the stored ones (after rt_make_material); `#` starts a comment.
+ * rt_scene_load allocates the two arrays with malloc (release with rt_scene_free).
+ * Both return 0, or -1 on an I/O or syntax error. */
+int rt_scene_save(const char* path, const rt_sphere* spheres, unsigned sphNum,
+                  const rt_light* lights, unsigned lgtNum);
+int rt_scene_load(const char* path, rt_sphere** spheres, unsigned* sphNum,
+                  rt_light** lights, unsigned* lgtNum);
+void rt_scene_free(void* arrayFromLoad);
+
 #ifdef __cplusplus
 }
 #endif

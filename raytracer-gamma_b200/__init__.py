@@ -126,6 +126,10 @@ C_ABI = [
      [_P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     ("rt_scene_default", None, [_P, _P]),
     ("rt_scene_synth", ctypes.c_int, [ctypes.c_uint, ctypes.c_uint, ctypes.c_uint64, _P, _P]),
+    ("rt_scene_save", ctypes.c_int, [ctypes.c_char_p, _P, ctypes.c_uint, _P, ctypes.c_uint]),
+    ("rt_scene_load", ctypes.c_int, [ctypes.c_char_p, ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_uint),
+                                     ctypes.POINTER(_P), ctypes.POINTER(ctypes.c_uint)]),
+    ("rt_scene_free", None, [_P]),
 ]
 
 _LIB = None
@@ -179,6 +183,34 @@ def synth_scene(n: int, lights: int = 4, seed: int = 0):
     rc = _lib().rt_scene_synth(n, lights, seed, sph.ctypes.data, lgt.ctypes.data)
     if rc:
         raise ValueError("rt_scene_synth: bad arguments")
+    return sph, lgt
+
+
+def save_scene(path, spheres: np.ndarray, lights: np.ndarray) -> None:
+    spheres = np.ascontiguousarray(spheres)
+    lights = np.ascontiguousarray(lights)
+    rc = _lib().rt_scene_save(str(path).encode(), spheres.ctypes.data if len(spheres) else None, len(spheres),
+                              lights.ctypes.data if len(lights) else None, len(lights))
+    if rc:
+        raise OSError(f"rt_scene_save({path}) failed")
+
+
+def load_scene(path):
+    ps, pl = _P(), _P()
+    ns, nl = ctypes.c_uint(0), ctypes.c_uint(0)
+    rc = _lib().rt_scene_load(str(path).encode(), ctypes.byref(ps), ctypes.byref(ns), ctypes.byref(pl), ctypes.byref(nl))
+    if rc:
+        raise OSError(f"rt_scene_load({path}) failed")
+    try:
+        sph = np.zeros(ns.value, SPHERE_DTYPE)
+        lgt = np.zeros(nl.value, LIGHT_DTYPE)
+        if ns.value:
+            ctypes.memmove(sph.ctypes.data, ps, sph.nbytes)
+        if nl.value:
+            ctypes.memmove(lgt.ctypes.data, pl, lgt.nbytes)
+    finally:
+        _lib().rt_scene_free(ps)
+        _lib().rt_scene_free(pl)
     return sph, lgt
 
 

@@ -8,7 +8,7 @@
  *
  *   rt_gamma [--width W] [--height H] [--alias A] [--zoom Z] [--depth S]
  *            [--spheres N] [--lights L] [--seed K] [--device D] [--list]
- *            [--out file.ppm] [--frames F]
+ *            [--out file.ppm] [--frames F] [--scene file] [--save-scene file]
  */
 #include <chrono>
 #include <cstdio>
@@ -46,6 +46,7 @@ int main(int argc, char** argv) {
   unsigned long long seed = 0;
   int device = 0;
   std::string out = "testPPM.ppm";           /* main.cpp:501 */
+  std::string sceneFile, saveScene;
 
   for (int i = 1; i < argc; ++i) {
     auto need = [&](const char* flag) -> const char* {
@@ -63,6 +64,8 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--device")) device = atoi(need("--device"));
     else if (!strcmp(argv[i], "--frames")) frames = (unsigned)atoi(need("--frames"));
     else if (!strcmp(argv[i], "--out")) out = need("--out");
+    else if (!strcmp(argv[i], "--scene")) sceneFile = need("--scene");
+    else if (!strcmp(argv[i], "--save-scene")) saveScene = need("--save-scene");
     else if (!strcmp(argv[i], "--list")) {
       const int n = rt_cuda_device_count();
       printf("%d CUDA device(s)\n", n);
@@ -73,7 +76,8 @@ int main(int argc, char** argv) {
       return 0;
     } else {
       fprintf(stderr, "usage: %s [--width W] [--height H] [--alias A] [--zoom Z] [--depth S] "
-                      "[--spheres N] [--lights L] [--seed K] [--device D] [--frames F] [--out file.ppm] [--list]\n",
+                      "[--spheres N] [--lights L] [--seed K] [--device D] [--frames F] [--out file.ppm] [--scene file] "
+                      "[--save-scene file] [--list]\n",
               argv[0]);
       return EXIT_FAILURE;
     }
@@ -82,7 +86,15 @@ int main(int argc, char** argv) {
   /* the scene: the reference literal, or synth(N, L, seed) */
   std::vector<rt_sphere> spheres;
   std::vector<rt_light> lights;
-  if (nSpheres == 0) {
+  if (!sceneFile.empty()) {
+    rt_sphere* s = nullptr; rt_light* l = nullptr; unsigned ns = 0, nl = 0;
+    if (rt_scene_load(sceneFile.c_str(), &s, &ns, &l, &nl) != 0) {
+      fprintf(stderr, "cannot read scene file %s\n", sceneFile.c_str());
+      return EXIT_FAILURE;
+    }
+    spheres.assign(s, s + ns); lights.assign(l, l + nl);
+    rt_scene_free(s); rt_scene_free(l);
+  } else if (nSpheres == 0) {
     spheres.resize(RT_SCENE_DEFAULT_SPHERES);
     lights.resize(RT_SCENE_DEFAULT_LIGHTS);
     rt_scene_default(spheres.data(), lights.data());
@@ -93,6 +105,12 @@ int main(int argc, char** argv) {
       fprintf(stderr, "bad synthetic scene parameters\n");
       return EXIT_FAILURE;
     }
+  }
+
+  if (!saveScene.empty() &&
+      rt_scene_save(saveScene.c_str(), spheres.data(), (unsigned)spheres.size(), lights.data(), (unsigned)lights.size()) != 0) {
+    fprintf(stderr, "cannot write scene file %s\n", saveScene.c_str());
+    return EXIT_FAILURE;
   }
 
   rt_cuda_ctx* ctx = nullptr;

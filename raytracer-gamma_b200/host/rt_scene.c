@@ -1,5 +1,7 @@
 /* rt_scene.c — see include/rt_scene.h.  Plain C, no device code. */
 #include <math.h>
+#include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 #include "rt_scene.h"
 
@@ -82,5 +84,64 @@ int rt_scene_synth(unsigned sphNum, unsigned lgtNum, uint64_t seed,
     lights[l].pos = vec3(lightPos[l][0], lightPos[l][1], lightPos[l][2]);
     lights[l].col = vec3(0.5f, 0.5f, 0.5f);
   }
+  return 0;
+}
+
+int rt_scene_save(const char* path, const rt_sphere* spheres, unsigned sphNum,
+                  const rt_light* lights, unsigned lgtNum) {
+  if (!path || (sphNum && !spheres) || (lgtNum && !lights)) return -1;
+  FILE* f = fopen(path, "w");
+  if (!f) return -1;
+  fprintf(f, "rtgamma-scene 1\n# %u spheres, %u lights\n", sphNum, lgtNum);
+  for (unsigned i = 0; i < sphNum; ++i) {
+    const rt_sphere* s = &spheres[i];
+    fprintf(f, "sphere %a %a %a %a  %a %a %a  %a %a %a  %a %a\n", s->pos.x, s->pos.y, s->pos.z, s->radius,
+            s->material.matteColour.x, s->material.matteColour.y, s->material.matteColour.z,
+            s->material.glossColour.x, s->material.glossColour.y, s->material.glossColour.z,
+            s->material.opacity, s->material.refractiveIndex);
+  }
+  for (unsigned l = 0; l < lgtNum; ++l)
+    fprintf(f, "light %a %a %a  %a %a %a\n", lights[l].pos.x, lights[l].pos.y, lights[l].pos.z,
+            lights[l].col.x, lights[l].col.y, lights[l].col.z);
+  const int bad = ferror(f);
+  return (fclose(f) == 0 && !bad) ? 0 : -1;
+}
+
+void rt_scene_free(void* p) { free(p); }
+
+int rt_scene_load(const char* path, rt_sphere** spheres, unsigned* sphNum,
+                  rt_light** lights, unsigned* lgtNum) {
+  if (!path || !spheres || !sphNum || !lights || !lgtNum) return -1;
+  *spheres = NULL; *lights = NULL; *sphNum = 0; *lgtNum = 0;
+  FILE* f = fopen(path, "r");
+  if (!f) return -1;
+  char line[1024];
+  unsigned ns = 0, nl = 0, capS = 0, capL = 0;
+  rt_sphere* S = NULL; rt_light* L = NULL;
+  int ok = 1, header = 0;
+  while (ok && fgets(line, sizeof line, f)) {
+    char* hash = strchr(line, '#');
+    if (hash) *hash = 0;
+    char tag[32];
+    if (sscanf(line, "%31s", tag) != 1) continue;           /* blank line */
+    if (!header) { int v = 0; ok = (!strcmp(tag, "rtgamma-scene") && sscanf(line, "%*s %d", &v) == 1 && v == 1); header = 1; continue; }
+    if (!strcmp(tag, "sphere")) {
+      float v[12];
+      if (sscanf(line, "%*s %f %f %f %f %f %f %f %f %f %f %f %f", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5], &v[6],
+                 &v[7], &v[8], &v[9], &v[10], &v[11]) != 12) { ok = 0; break; }
+      if (ns == capS) { capS = capS ? capS * 2 : 64; rt_sphere* t = (rt_sphere*)realloc(S, capS * sizeof *t); if (!t) { ok = 0; break; } S = t; }
+      memcpy(&S[ns++], v, sizeof(rt_sphere));               /* rt_sphere is 12 packed floats in this order */
+    } else if (!strcmp(tag, "light")) {
+      float v[6];
+      if (sscanf(line, "%*s %f %f %f %f %f %f", &v[0], &v[1], &v[2], &v[3], &v[4], &v[5]) != 6) { ok = 0; break; }
+      if (nl == capL) { capL = capL ? capL * 2 : 8; rt_light* t = (rt_light*)realloc(L, capL * sizeof *t); if (!t) { ok = 0; break; } L = t; }
+      memcpy(&L[nl++], v, sizeof(rt_light));
+    } else {
+      ok = 0;
+    }
+  }
+  fclose(f);
+  if (!ok || !header) { free(S); free(L); return -1; }
+  *spheres = S; *sphNum = ns; *lights = L; *lgtNum = nl;
   return 0;
 }

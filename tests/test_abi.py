@@ -77,3 +77,25 @@ def test_local_rows_partition(pkg):
         rows = [pkg.local_rows(H, 4, g, G) for g in range(G)]
         allr = np.sort(np.concatenate(rows))
         assert np.array_equal(allr, np.arange(H))
+
+
+def test_scene_file_round_trip(pkg, tmp_path):
+    """Hex-float scene files reproduce the arrays bit for bit (incl. awkward values)."""
+    sph, lgt = pkg.synth_scene(300, 4, seed=9)
+    sph["pos"][3] = (np.float32(1e-40), -0.0, np.float32(3.4e38))     # denormal, -0, near FLT_MAX
+    p = tmp_path / "scene.txt"
+    pkg.save_scene(p, sph, lgt)
+    s2, l2 = pkg.load_scene(p)
+    assert np.array_equal(sph.view(np.uint32), s2.view(np.uint32)) and np.array_equal(lgt.view(np.uint32), l2.view(np.uint32))
+    text = p.read_text()
+    assert text.startswith("rtgamma-scene 1") and text.count("\nsphere ") == 300 and text.count("\nlight ") == 4
+    # comments / blank lines are skipped, malformed files are refused
+    p.write_text("rtgamma-scene 1\n\n# a comment\nlight 0x1p+0 0 0  1 1 1   # trailing comment\n")
+    s3, l3 = pkg.load_scene(p)
+    assert len(s3) == 0 and len(l3) == 1 and l3["pos"][0][0] == 1.0
+    for bad in ("", "rtgamma-scene 2\n", "rtgamma-scene 1\nsphere 1 2 3\n", "rtgamma-scene 1\ntriangle 1 2 3\n"):
+        p.write_text(bad)
+        with pytest.raises(OSError):
+            pkg.load_scene(p)
+    with pytest.raises(OSError):
+        pkg.load_scene(tmp_path / "missing.txt")

@@ -222,3 +222,22 @@ def test_host_program_writes_the_reference_ppm(pkg, tmp_path):
     assert hashlib.md5(out.read_bytes()).hexdigest() == FACTS["default_800x600_a3_s6"]["ppm_md5"]
     res = subprocess.run([str(pkg.HOST_BIN), "--list"], capture_output=True, text=True, timeout=60)
     assert res.returncode == 0 and "CUDA device" in res.stdout
+
+
+def test_full_size_properties_config4(pkg, orc_mod, oracle, gpu):
+    """BASELINE config 4 at full size (7680x4320, 1024 spheres, 4 spp, depth 8): 64 rows spread
+    over the frame against the oracle (the oracle needs ~0.3 s per row on 16 cores), the
+    8-GPU strip partition reassembled on one GPU, and size-independent properties."""
+    sph, lgt = pkg.synth_scene(1024, 4)
+    W, H, S, alias = 7680, 4320, 8, 2.0
+    fb, mx, st = _render(gpu, sph, lgt, W, H, -4.0, alias, S)
+    rows = (33, 64, 67)
+    ref, ctr = oracle.render(sph, lgt, W, H, -4.0, alias, S, rows=rows)
+    got = fb[rows[0]::rows[2]][:rows[1]]
+    _assert_parity(orc_mod, oracle, ref, got)
+    assert st["samples"] == W * H * 4 and mx == oracle.max_colour(fb)
+    # shard 5 of 8 (16-row strips) is the same pixels as the corresponding rows of the full frame
+    gpu.render_strips(W, H, -4.0, alias, S, 16, 5, 8)
+    part, _ = gpu.readback()
+    mine = pkg.local_rows(H, 16, 5, 8)
+    assert np.array_equal(orc_mod.canon(part), orc_mod.canon(fb[mine]))
