@@ -163,6 +163,9 @@ def sample_rows(H: int, count: int):
     return begin, count, step
 
 
+_COUNTER_CACHE: dict = {}
+
+
 def cpu_leg(om, sph, lgt, W, H, alias, S, seconds: float, threads: int = 0):
     """Time the reference CPU implementation (oracle/_ref when present, else the C port) on
     a bounded sample of rows of the SAME workload.  -> dict, (rows, framebuffer)"""
@@ -183,7 +186,10 @@ def cpu_leg(om, sph, lgt, W, H, alias, S, seconds: float, threads: int = 0):
         count = int(min(H, max(count + cores, count * grow)))
         count -= count % cores
     if kind == "reference":   # the reference has no counters: count the same rows with the port, untimed
-        _, ctr = port.render(sph, lgt, W, H, ZOOM, alias, S, rows=rows, threads=threads)
+        key = (W, H, alias, S, rows, len(sph), len(lgt))
+        if key not in _COUNTER_CACHE:
+            _COUNTER_CACHE[key] = port.render(sph, lgt, W, H, ZOOM, alias, S, rows=rows, threads=threads)[1]
+        ctr = _COUNTER_CACHE[key]
     n = len(sph)
     rays = ctr["rays"]
     out = {

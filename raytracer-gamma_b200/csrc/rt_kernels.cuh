@@ -33,7 +33,9 @@
 
 namespace rtg {
 
+#ifndef RT_BLOCK
 #define RT_BLOCK 256
+#endif
 #define RT_LIST_MAX 24
 #define RT_CONST_MAX_SPHERES 1024
 #define RT_NUM_COUNTERS 24
