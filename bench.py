@@ -442,7 +442,8 @@ def run_ours(args):
                                / (st["kernel_ms"] * 1e-3) / 1e12,
             "passes": {"trace": st["passes_trace"], "shadow4": st["passes_shadow4"], "shadow2": st["passes_shadow2"],
                        "contain": st["passes_contain"]},
-            "lane_utilisation": st["active_lane_iters"] / max(1, st["lane_iters"]),
+            "lane_utilisation": (st["active_lane_iters"] / st["lane_iters"]) if st["lane_iters"] else None,
+            "engine": {1: "persistent multi-slot kernel", 2: "wavefront (filter + shade kernels)"}.get(st["engine"]),
             "launch": {"grid": st["grid"], "block": st["block"], "smem_bytes": st["smem_bytes"],
                        "staging": {1: "__constant__", 2: "shared (TMA bulk)"}.get(st["staging"])},
         }

@@ -73,6 +73,7 @@ typedef struct rt_cuda_stats {
   float    max_colour;      /* NaN-skipping max of this context's rows, 0 if all black              */
   uint32_t kernel_launches; /* kernels this library launched since the last render began            */
   uint32_t grid, block, smem_bytes, staging;   /* launch shape; staging 1 = __constant__, 2 = shared via TMA bulk */
+  uint32_t engine;          /* 1 = persistent multi-slot kernel, 2 = wavefront (filter + shade kernels) */
 } rt_cuda_stats;
 
 /* Open device `device` (cudaSetDevice ordinal).  *out receives the context. */
@@ -122,7 +123,8 @@ int rt_cuda_synchronize(rt_cuda_ctx* ctx);
 /* Tuning / debug switches: "staging" 0 auto | 1 __constant__ | 2 shared (TMA bulk);
  * "no_filter" 1 = exact test against every sphere; "blocks_per_sm" 0 auto;
  * "min_blocks" 0 auto | 2 | 3 = register-budget variant of the trace kernel;
- * "slots" 0 auto | 2 | 3 | 4 = pixels in flight per lane. */
+ * "slots" 0 auto | 2 | 3 | 4 = pixels in flight per lane;
+ * "engine" 0 auto | 1 persistent kernel | 2 wavefront; "pool" = wavefront samples in flight. */
 int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value);
 
 int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out);

@@ -84,7 +84,7 @@ class Stats(ctypes.Structure):
         ("kernel_ms", ctypes.c_float), ("max_colour", ctypes.c_float),
         ("kernel_launches", ctypes.c_uint32),
         ("grid", ctypes.c_uint32), ("block", ctypes.c_uint32), ("smem_bytes", ctypes.c_uint32),
-        ("staging", ctypes.c_uint32),
+        ("staging", ctypes.c_uint32), ("engine", ctypes.c_uint32),
     ]
 
     def as_dict(self) -> dict:

@@ -168,28 +168,46 @@ __device__ __forceinline__ f32x2 bq2(const Dir2& D, f32x2 cx, f32x2 cy, f32x2 cz
 /* Spheres per unrolled group of each pass.  Small groups keep the three hot loops inside
  * the instruction caches (they run concurrently on one SM in different warps). */
 #ifndef RT_GROUP_T
-#define RT_GROUP_T 8
+#define RT_GROUP_T 16
 #endif
-#ifndef RT_GROUP_S
-#define RT_GROUP_S 8
+#ifndef RT_GROUP_S4
+#define RT_GROUP_S4 8
+#endif
+#ifndef RT_GROUP_S2
+#define RT_GROUP_S2 16
 #endif
 #ifndef RT_GROUP_C
-#define RT_GROUP_C 8
+#define RT_GROUP_C 16
 #endif
 
-/* Turn the set bits of one group's combined candidate mask into list entries
- * (sub << 14 | sphere).  Sub-query `sub` owns bits [sub*BITS, sub*BITS+G); inside a field
- * bit (G-1-j) belongs to sphere base+j, so scanning from the top bit yields each
- * sub-query's spheres in increasing order.  A full list sets `overflow`: that lane then
- * resolves the pass exactly against every sphere (rare). */
-template <int BITS, int G>
+/* One group's sign bits are collected in ONE register: the loop shifts in, sphere by sphere,
+ * the sign of each of the lane's ND sub-queries (funnel shift, one instruction per test;
+ * every instruction that is not an FMA costs the FMA pipe an issue cycle, scripts/ubench_mix.cu).
+ * After the group, test (j, sub) sits at bit G*ND-1 - (j*ND + sub).  mask_of_sub gives the bits
+ * of one sub-query; gather turns the set bits of ~signs & mask into list entries
+ * (sub << 14 | sphere): scanning from the top bit yields each sub-query's spheres in
+ * increasing order.  A full list sets `overflow`: that lane then resolves the pass exactly
+ * against every sphere (rare). */
+template <int ND, int G>
+__host__ __device__ constexpr unsigned mask_of_sub(int sub) {
+  unsigned m = 0u;
+  for (int j = 0; j < G; ++j) m |= 1u << (G * ND - 1 - (j * ND + sub));
+  return m;
+}
+/* keeps a loop-invariant value in its register (the compiler otherwise rebuilds it from
+ * predicates / the constant bank on every trip, which costs issue slots in the hot loops) */
+__device__ __forceinline__ unsigned pin(unsigned v) { asm volatile("" : "+r"(v)); return v; }
+
+template <int ND, int G>
 __device__ __forceinline__ void gather(const WarpCtx& w, unsigned comb, uint32_t base, int& cnt,
                                        bool& overflow) {
+  static_assert(G * ND <= 32 && (ND & (ND - 1)) == 0, "one 32-bit register per group");
   while (comb) {
     const int b = 31 - __clz(comb);
     comb &= ~(1u << b);
     if (cnt < RT_LIST_MAX) {
-      const uint32_t sub = (uint32_t)b / BITS, j = (uint32_t)(G - 1) - ((uint32_t)b % BITS);
+      const uint32_t idx = (uint32_t)(G * ND - 1 - b);
+      const uint32_t sub = idx % ND, j = idx / ND;
       w.list[cnt * RT_BLOCK + w.tid] = (unsigned short)((sub << 14) | (base + j));
       ++cnt;
     } else {
@@ -248,7 +266,6 @@ template <bool USE_CONST>
 __device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                            int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_T;
-  static_assert(G <= 16, "two 16-bit mask fields");
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
   DirQ D0, D1;
   D0.ndx = D0.ndy = D0.ndz = D0.od = 0.f; D1 = D0;
@@ -263,31 +280,31 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slo
     live1 = make_dir(D1, slots[s1].qo, slots[s1].rayD);
     exact1 = live1 && (p.noFilter || !(origin_filterable(O1) && dir_filterable(D1)));
   }
-  const unsigned fld = (1u << G) - 1u;
-  const unsigned msk = ((live0 && !exact0) ? fld : 0u) | ((live1 && !exact1) ? (fld << 16) : 0u);
+  constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
+  const unsigned msk = pin(((live0 && !exact0) ? m0 : 0u) | ((live1 && !exact1) ? m1 : 0u));
   const Origin2 OO = pack_origin(O0, O1);
   const Dir2 DD = pack_dir(D0, D1);
   int cnt = 0;
   bool overflow = false;
   RT_TICK(1);
   if (!p.noFilter) {
-    const uint32_t groups = w.nPad / G;
-    for (uint32_t g = 0; g < groups; ++g) {
-      unsigned k0 = 0, k1 = 0;
+    const uint32_t nPad = pin(w.nPad);
+    for (uint32_t base = 0; base < nPad; base += G) {
+      unsigned k = 0;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, g * G + j);
+        const float4_ s = load_filt<USE_CONST>(w, base + j);
         const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
         const f32x2 b = bq2(DD, cx, cy, cz);
         f32x2 ch = fma2(OO.px, cx, pk1(s.w));
         ch = fma2(OO.py, cy, ch);
         ch = fma2(OO.pz, cz, ch);
         const f32x2 d = fma2(b, b, sub2(OO.nq, ch));     /* both rays: sign set <=> certain miss */
-        k0 = __funnelshift_l(__float_as_uint(lo_of(d)), k0, 1);
-        k1 = __funnelshift_l(__float_as_uint(hi_of(d)), k1, 1);
+        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
       }
-      const unsigned comb = ~(k0 | (k1 << 16)) & msk;
-      if (comb) gather<16, G>(w, comb, g * G, cnt, overflow);
+      const unsigned comb = ~k & msk;
+      if (comb) gather<2, G>(w, comb, base, cnt, overflow);
     }
   }
   float t0 = 1000.f, t1 = 1000.f;
@@ -323,8 +340,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slo
 template <bool USE_CONST, int ND>
 __device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                             Counters& ctr) {
-  constexpr int G = RT_GROUP_S;
-  static_assert(G * ND <= 32, "ND mask fields of G bits");
+  constexpr int G = (ND == 4) ? RT_GROUP_S4 : RT_GROUP_S2;
   OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
   DirQ D[ND];
   unsigned live = 0u, exact = 0u;
@@ -366,7 +382,8 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Sl
   }
   unsigned msk = 0u;
 #pragma unroll
-  for (int k = 0; k < ND; ++k) msk |= (((live & ~exact) >> k) & 1u) ? (((1u << G) - 1u) << (k * G)) : 0u;
+  for (int k = 0; k < ND; ++k) msk |= (((live & ~exact) >> k) & 1u) ? mask_of_sub<ND, G>(k) : 0u;
+  msk = pin(msk);
   static_assert(ND % 2 == 0, "rays are processed as packed pairs");
   Dir2 DP[ND / 2];
 #pragma unroll
@@ -375,29 +392,24 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Sl
   bool overflow = false;
   RT_TICK(1);
   if (!p.noFilter) {
-    const uint32_t groups = w.nPad / G;
-    for (uint32_t g = 0; g < groups; ++g) {
-      unsigned sk[ND];
-#pragma unroll
-      for (int k = 0; k < ND; ++k) sk[k] = 0u;
+    const uint32_t nPad = pin(w.nPad);
+    for (uint32_t base = 0; base < nPad; base += G) {
+      unsigned sk = 0u;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, g * G + j);
+        const float4_ s = load_filt<USE_CONST>(w, base + j);
         const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
         const f32x2 e = pk1(ex_sub(O.nq, filter_ch(O, s)));   /* -q - ch: once per sphere, all rays share the origin */
 #pragma unroll
         for (int k = 0; k < ND / 2; ++k) {
           const f32x2 b = bq2(DP[k], cx, cy, cz);
           const f32x2 d = fma2(b, b, e);
-          sk[2 * k] = __funnelshift_l(__float_as_uint(lo_of(d)), sk[2 * k], 1);
-          sk[2 * k + 1] = __funnelshift_l(__float_as_uint(hi_of(d)), sk[2 * k + 1], 1);
+          sk = __funnelshift_l(__float_as_uint(lo_of(d)), sk, 1);
+          sk = __funnelshift_l(__float_as_uint(hi_of(d)), sk, 1);
         }
       }
-      unsigned comb = 0u;
-#pragma unroll
-      for (int k = 0; k < ND; ++k) comb |= sk[k] << (k * G);
-      comb = ~comb & msk;
-      if (comb) gather<G, G>(w, comb, g * G, cnt, overflow);
+      const unsigned comb = ~sk & msk;
+      if (comb) gather<ND, G>(w, comb, base, cnt, overflow);
     }
   }
   unsigned blocked = 0u;
@@ -440,33 +452,32 @@ template <bool USE_CONST>
 __device__ __forceinline__ void pass_contain(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                              int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_C;
-  static_assert(G <= 16, "two 16-bit mask fields");
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
   bool exact0 = false, exact1 = false;
   if (s0 >= 0) { O0 = make_origin(slots[s0].qo); exact0 = p.noFilter || !origin_filterable(O0); }
   if (s1 >= 0) { O1 = make_origin(slots[s1].qo); exact1 = p.noFilter || !origin_filterable(O1); }
-  const unsigned fld = (1u << G) - 1u;
-  const unsigned msk = ((s0 >= 0 && !exact0) ? fld : 0u) | ((s1 >= 0 && !exact1) ? (fld << 16) : 0u);
+  constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
+  const unsigned msk = pin(((s0 >= 0 && !exact0) ? m0 : 0u) | ((s1 >= 0 && !exact1) ? m1 : 0u));
   const Origin2 OO = pack_origin(O0, O1);
   int cnt = 0;
   bool overflow = false;
   RT_TICK(1);
   if (!p.noFilter) {
-    const uint32_t groups = w.nPad / G;
-    for (uint32_t g = 0; g < groups; ++g) {
-      unsigned k0 = 0, k1 = 0;
+    const uint32_t nPad = pin(w.nPad);
+    for (uint32_t base = 0; base < nPad; base += G) {
+      unsigned k = 0;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, g * G + j);
+        const float4_ s = load_filt<USE_CONST>(w, base + j);
         f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
         ch = fma2(OO.py, pk1(s.y), ch);
         ch = fma2(OO.pz, pk1(s.z), ch);
         const f32x2 d = sub2(OO.nq, ch);                  /* both probes: sign set <=> certainly outside */
-        k0 = __funnelshift_l(__float_as_uint(lo_of(d)), k0, 1);
-        k1 = __funnelshift_l(__float_as_uint(hi_of(d)), k1, 1);
+        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
       }
-      const unsigned comb = ~(k0 | (k1 << 16)) & msk;
-      if (comb) gather<16, G>(w, comb, g * G, cnt, overflow);
+      const unsigned comb = ~k & msk;
+      if (comb) gather<2, G>(w, comb, base, cnt, overflow);
     }
   }
   int h0 = -1, h1 = -1;

@@ -11,6 +11,7 @@
 
 #include "rt_cuda.h"
 #include "rt_kernels.cuh"
+#include "rt_wavefront.cuh"
 #include "rt_soa.h"
 
 using namespace rtg;
@@ -47,6 +48,15 @@ struct rt_cuda_ctx {
 
   /* options */
   int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0, slots = 0, prefetch = 0;
+  int engine = 0;                  /* 0 auto, 1 persistent kernel, 2 wavefront */
+  long pool = 0;                   /* wavefront: samples in flight (0 = default) */
+
+  /* wavefront pool */
+  uint32_t* dPool = nullptr; size_t poolCap = 0;      /* words */
+  Frame* dStacks = nullptr; size_t stacksCap = 0;     /* samples */
+  uint32_t* dQueues = nullptr; size_t queuesCap = 0;  /* entries */
+  uint32_t* dCounts = nullptr;                        /* [2][4] */
+  uint32_t* hCounts = nullptr;                        /* pinned [4] */
 
   /* stats */
   rt_cuda_stats stats{};
@@ -134,6 +144,8 @@ extern "C" void rt_cuda_destroy(rt_cuda_ctx* ctx) {
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   cudaFree(ctx->dScene); cudaFree(ctx->dFb); cudaFree(ctx->dPacked); cudaFree(ctx->dRgb8); cudaFree(ctx->dSamples);
+  cudaFree(ctx->dPool); cudaFree(ctx->dStacks); cudaFree(ctx->dQueues); cudaFree(ctx->dCounts);
+  if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
   cudaFree(ctx->dWork); cudaFree(ctx->dCounters);
   if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
@@ -164,6 +176,8 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!ctx || !key) return RT_CUDA_ERR_INVALID_ARG;
   if (!strcmp(key, "staging")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->staging = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
+  if (!strcmp(key, "engine")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->engine = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "pool")) { if (value < 0) return RT_CUDA_ERR_INVALID_ARG; ctx->pool = value; return RT_CUDA_OK; }
   if (!strcmp(key, "prefetch")) { ctx->prefetch = value ? 1 : 0; return RT_CUDA_OK; }
   if (!strcmp(key, "slots")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->slots = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "min_blocks")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->minBlocks = (int)value; return RT_CUDA_OK; }
@@ -206,6 +220,95 @@ static int ensure_frame(rt_cuda_ctx* ctx, size_t pixels) {
     CU(cudaMalloc(&ctx->dFb, pixels * sizeof(float4)));
     ctx->fbCap = pixels;
   }
+  return RT_CUDA_OK;
+}
+
+#define RT_DEFAULT_POOL (1l << 21)          /* samples in flight of the wavefront engine */
+
+/* The wavefront engine: alternate the pure filter kernels and the shade kernel over a pool
+ * of samples until the frame's work counter and all queues are drained (rt_wavefront.cuh).
+ * The host only launches; it looks at the queue lengths every few rounds to know when to stop. */
+static int render_wavefront(rt_cuda_ctx* ctx, const TraceParams& tp, uint32_t spp, size_t pixels) {
+  const uint64_t totalWork = (uint64_t)pixels * spp;
+  if (totalWork >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
+  uint64_t P = (uint64_t)(ctx->pool > 0 ? ctx->pool : RT_DEFAULT_POOL);
+  if (P > totalWork) P = totalWork;
+  if (P * RT_SLOT_WORDS > ctx->poolCap) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dPool); ctx->dPool = nullptr; ctx->poolCap = 0;
+    CU(cudaMalloc(&ctx->dPool, P * RT_SLOT_WORDS * sizeof(uint32_t)));
+    ctx->poolCap = P * RT_SLOT_WORDS;
+  }
+  if (P > ctx->stacksCap) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dStacks); ctx->dStacks = nullptr; ctx->stacksCap = 0;
+    CU(cudaMalloc(&ctx->dStacks, P * RT_MAX_STACK * sizeof(Frame)));
+    ctx->stacksCap = P;
+  }
+  if (P * 6 > ctx->queuesCap) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dQueues); ctx->dQueues = nullptr; ctx->queuesCap = 0;
+    CU(cudaMalloc(&ctx->dQueues, P * 6 * sizeof(uint32_t)));
+    ctx->queuesCap = P * 6;
+  }
+  if (!ctx->dCounts) CU(cudaMalloc(&ctx->dCounts, 8 * sizeof(uint32_t)));
+  if (!ctx->hCounts) CU(cudaMallocHost(&ctx->hCounts, 4 * sizeof(uint32_t)));
+
+  WfParams wp;
+  wp.sc = tp.sc; wp.cam = tp.cam;
+  wp.st = ctx->dPool; wp.stacks = ctx->dStacks; wp.queues = ctx->dQueues; wp.counts = ctx->dCounts;
+  wp.P = (uint32_t)P; wp.cur = 0;
+  wp.fb = tp.fb; wp.samples = tp.samples; wp.spp = spp;
+  wp.workCounter = tp.workCounter; wp.maxBits = tp.maxBits; wp.counters = tp.counters;
+  wp.localRows = tp.localRows; wp.stripRows = tp.stripRows; wp.stripFirst = tp.stripFirst; wp.stripStride = tp.stripStride;
+  wp.totalWork = (uint32_t)totalWork;
+  wp.noFilter = tp.noFilter;
+
+  const size_t smem = 16 + (size_t)ctx->nPad * 16 + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
+                      + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
+  CU(cudaFuncSetAttribute(wf_filter<K_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaFuncSetAttribute(wf_filter<K_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  CU(cudaFuncSetAttribute(wf_filter<K_CONTAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int perSM = 0;
+  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wf_filter<K_SHADOW>, RT_BLOCK, smem));
+  if (perSM < 1) return RT_CUDA_ERR_TOO_LARGE;
+  const uint32_t gridF = (uint32_t)ctx->smCount * (uint32_t)perSM;
+  const uint32_t gridS = (uint32_t)ctx->smCount * 16u;
+
+  /* the first P work items are handed out by wf_spawn; the work counter continues from P */
+  const uint32_t init[8] = {(uint32_t)P, 0, 0, 0, 0, 0, 0, 0};
+  CU(cudaMemcpyAsync(ctx->dCounts, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
+  const uint32_t first = (uint32_t)P;
+  CU(cudaMemcpyAsync(tp.workCounter, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
+  CU(cudaStreamSynchronize(ctx->stream));          /* `init` / `first` are stack variables */
+
+  CU(cudaEventRecord(ctx->ev0, ctx->stream));
+  wf_spawn<<<(uint32_t)((P + 255) / 256), 256, 0, ctx->stream>>>(wp);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  const int CHECK = 4;
+  for (int round = 1;; ++round) {
+    wf_filter<K_TRACE><<<gridF, RT_BLOCK, smem, ctx->stream>>>(wp);
+    wf_filter<K_SHADOW><<<gridF, RT_BLOCK, smem, ctx->stream>>>(wp);
+    wf_filter<K_CONTAIN><<<gridF, RT_BLOCK, smem, ctx->stream>>>(wp);
+    CU(cudaMemsetAsync(ctx->dCounts + (wp.cur ^ 1u) * 4u, 0, 4 * sizeof(uint32_t), ctx->stream));
+    wf_shade<<<gridS, 128, 0, ctx->stream>>>(wp, K_TRACE);
+    wf_shade<<<gridS, 128, 0, ctx->stream>>>(wp, K_SHADOW);
+    wf_shade<<<gridS, 128, 0, ctx->stream>>>(wp, K_CONTAIN);
+    CU(cudaGetLastError());
+    ctx->launches += 6;
+    wp.cur ^= 1u;
+    if (round % CHECK == 0) {
+      CU(cudaMemcpyAsync(ctx->hCounts, ctx->dCounts + wp.cur * 4u, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaStreamSynchronize(ctx->stream));
+      if ((ctx->hCounts[0] | ctx->hCounts[1] | ctx->hCounts[2]) == 0u) break;
+    }
+    if (round > (1 << 22)) return RT_CUDA_ERR_CUDA;   /* cannot happen: every round retires work */
+  }
+  CU(cudaEventRecord(ctx->ev1, ctx->stream));
+  ctx->timed = true;
+  ctx->stats.grid = gridF; ctx->stats.block = RT_BLOCK; ctx->stats.smem_bytes = (uint32_t)smem;
+  ctx->stats.staging = 2;
   return RT_CUDA_OK;
 }
 
@@ -273,6 +376,22 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   }
   p.noFilter = ctx->noFilter;
   p.prefetch = ctx->prefetch;
+
+  /* engine choice: the wavefront engine (separate filter / shade kernels) is opt-in */
+  int engine = ctx->engine;
+  if (engine == 0) engine = 1;    /* the persistent kernel is faster at every size measured */
+  if (engine == 2 && ctx->n > 0) {
+    int rc = render_wavefront(ctx, p, spp, pixels);
+    if (rc) return rc;
+    ctx->stats.engine = 2;
+    if (spp > 1) {
+      combine_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->dSamples, ctx->dFb, (uint32_t)pixels, spp, ctx->dWork + 1);
+      CU(cudaGetLastError());
+      ctx->launches += 1;
+    }
+    return RT_CUDA_OK;
+  }
+  ctx->stats.engine = 1;
 
   /* staging choice: __constant__ broadcast for small scenes, shared memory (TMA bulk) otherwise */
   int staging = ctx->staging;

@@ -9,13 +9,12 @@ print(pkg.device_info(0))
 r = pkg.Renderer(0)
 print("ffma_peak TFLOP/s:", [round(r.ffma_peak(8192), 2) for _ in range(3)])
 cases = [
+    ("default 1080p a1 s4", pkg.default_scene(), 1920, 1080, 1.0, 4, {}),
     ("synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {}),
     ("synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {}),
-    ("synth1024 4K a1 s8 mb4", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4}),
-    ("synth1024 4K a1 s8 mb4 slots2", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 4, "slots": 2}),
-    ("synth1024 4K a1 s8 mb3 slots3", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"min_blocks": 3, "slots": 3}),
-    ("synth1024 4K a1 s8 1blk", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"blocks_per_sm": 1}),
-    ("synth1024 4K a1 s8 slots2", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"slots": 2}),
+    ("synth1024 4K a2 s8", pkg.synth_scene(1024, 4), 3840, 2160, 2.0, 8, {}),
+    ("synth4096 2K a1 s8", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {}),
+    ("wavefront s1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"engine": 2}),
 ]
 if len(sys.argv) > 1:
     cases = [c for c in cases if any(a in c[0] for a in sys.argv[1:])]

@@ -120,7 +120,8 @@ def test_staging_and_filter_variants_agree(pkg, orc_mod, gpu):
     sph, lgt = pkg.synth_scene(200, 4, seed=3)
     base, _, st0 = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8)
     for opts in ({"staging": 1}, {"staging": 2}, {"no_filter": 1}, {"blocks_per_sm": 1}, {"slots": 2}, {"slots": 3},
-                 {"min_blocks": 3}, {"min_blocks": 4}, {"prefetch": 1}):
+                 {"min_blocks": 3}, {"min_blocks": 4}, {"prefetch": 1}, {"engine": 1}, {"engine": 2},
+                 {"engine": 2, "pool": 777}, {"engine": 2, "no_filter": 1}):
         fb, _, st = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8, **opts)
         assert np.array_equal(orc_mod.canon(fb), orc_mod.canon(base)), opts
         assert st["rays"] == st0["rays"]
@@ -154,15 +155,37 @@ def test_edge_cases(pkg, orc_mod, oracle, gpu):
     fresh.close()
 
 
+@pytest.mark.parametrize("engine", [1, 2])
+def test_both_engines_match_oracle(pkg, orc_mod, oracle, gpu, engine):
+    """The persistent kernel and the wavefront engine are two schedules of the same per-sample
+    arithmetic: each is bit-exact against the oracle, single- and multi-sample, whole frame and strips."""
+    for (sph, lgt), (W, H, alias, S) in [(pkg.default_scene(), (200, 150, 3.0, 6)),
+                                          (pkg.synth_scene(300, 4, seed=4), (160, 90, 2.0, 8)),
+                                          (pkg.synth_scene(64, 2, seed=8), (97, 61, 1.0, 5))]:
+        fb, mx, st = _render(gpu, sph, lgt, W, H, -4.0, alias, S, engine=engine, pool=5000)
+        assert st["engine"] == engine
+        ref, ctr = oracle.render(sph, lgt, W, H, -4.0, alias, S)
+        _assert_parity(orc_mod, oracle, ref, fb)
+        for k in ("rays", "shadow_rays", "contain_queries", "contain_tests", "samples"):
+            assert st[k] == ctr[k], k
+        assert mx == oracle.max_colour(ref)
+        gpu.set_option("engine", engine)
+        gpu.render_strips(W, H, -4.0, alias, S, 8, 1, 3)
+        part, _ = gpu.readback()
+        gpu.set_option("engine", 0)
+        assert np.array_equal(orc_mod.canon(part), orc_mod.canon(fb[pkg.local_rows(H, 8, 1, 3)]))
+
+
 def test_rare_paths(pkg, orc_mod, oracle, gpu):
     """> 4 lights (several shadow batches), candidate-list overflow, non-finite filter records,
     the largest scene the library accepts."""
     from test_hostsim import _stress_scenes
     for name, (sph, lgt) in _stress_scenes(pkg).items():
-        fb, mx, st = _render(gpu, sph, lgt, 96, 64, -4.0, 1.0, 8)
         ref, ctr = oracle.render(sph, lgt, 96, 64, -4.0, 1.0, 8)
-        _assert_parity(orc_mod, oracle, ref, fb)
-        assert st["rays"] == ctr["rays"] and st["shadow_rays"] == ctr["shadow_rays"], name
+        for engine in (1, 2):
+            fb, mx, st = _render(gpu, sph, lgt, 96, 64, -4.0, 1.0, 8, engine=engine)
+            _assert_parity(orc_mod, oracle, ref, fb)
+            assert st["rays"] == ctr["rays"] and st["shadow_rays"] == ctr["shadow_rays"], (name, engine)
     sph, lgt = pkg.synth_scene(12288, 4, seed=2)          # RT_CUDA_MAX_SPHERES
     fb, mx, st = _render(gpu, sph, lgt, 48, 27, -4.0, 1.0, 8)
     ref, ctr = oracle.render(sph, lgt, 48, 27, -4.0, 1.0, 8)
