@@ -74,6 +74,9 @@ typedef struct rt_cuda_stats {
   uint32_t kernel_launches; /* kernels this library launched since the last render began            */
   uint32_t grid, block, smem_bytes, staging;   /* launch shape; staging 1 = __constant__, 2 = shared via TMA bulk */
   uint32_t engine;          /* 1 = persistent multi-slot kernel, 2 = wavefront (filter + shade kernels) */
+  uint32_t accel;           /* 1 = this frame used the two-level cluster filter (option "accel")    */
+  uint32_t clusters;        /* ... over this many sphere clusters                                   */
+  uint32_t reserved_;
 } rt_cuda_stats;
 
 /* Open device `device` (cudaSetDevice ordinal).  *out receives the context. */

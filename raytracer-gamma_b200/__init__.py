@@ -85,6 +85,7 @@ class Stats(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint32),
         ("grid", ctypes.c_uint32), ("block", ctypes.c_uint32), ("smem_bytes", ctypes.c_uint32),
         ("staging", ctypes.c_uint32), ("engine", ctypes.c_uint32),
+        ("accel", ctypes.c_uint32), ("clusters", ctypes.c_uint32), ("reserved_", ctypes.c_uint32),
     ]
 
     def as_dict(self) -> dict:

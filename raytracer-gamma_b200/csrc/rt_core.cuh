@@ -104,6 +104,11 @@ struct SceneView {
   const float4_* lpos;   /* [nl]   {pos.xyz, 0}                                        */
   const float4_* lcol;   /* [nl]   {col.rgb, 0}                                        */
   uint32_t n, nPad, nl;
+  /* optional two-level form (see "Cluster filter"): cfilt | mfilt | midx are contiguous */
+  const float4_* cfilt;  /* [ncPad] filter record of each cluster's bounding sphere     */
+  const float4_* mfilt;  /* [nc*RT_CLUSTER] the members' filter records, cluster by cluster */
+  const unsigned short* midx;  /* [nc*RT_CLUSTER] the members' sphere indices            */
+  uint32_t nc, ncPad;
 };
 
 /* ---- Filter ---------------------------------------------------------------
@@ -134,6 +139,27 @@ struct SceneView {
  */
 #define RT_KAPPA 7.62939453125e-06f   /* 2^-17 */
 
+/* ---- Cluster filter (optional accelerated mode) ---------------------
+ * The spheres are grouped (host side, rt_soa.h) into spatial clusters of RT_CLUSTER members.
+ * Each cluster gets the filter record of a bounding sphere (C, R); a query first runs the
+ * filter over the clusters and then over the members of the clusters it could not rule out.
+ * Exactness needs: "the reference reports a hit of member i  =>  cluster(i) is not ruled out".
+ *   (1) a reference hit means, in exact arithmetic, dist(line, c_i)^2 <= r_i^2 + eta_i with
+ *       eta_i <= 64u (|o|^2 + |c_i|^2 + r_i^2)   (the 17u+4u radicand terms of "Filter", u = 2^-24);
+ *       the containment probe of raytracer.h:245-270 adds 2.1e-6 r_i + 1e-12;
+ *   (2) dist(line, C) <= dist(line, c_i) + D_i with D_i = |C - c_i|, so
+ *       dist(line, C)^2 <= (r_i + D_i)^2 + D_i^2/32 + 33 eta_i            (2ab <= a^2/32 + 32 b^2);
+ *   (3) the cluster record is the ordinary filter record of (C, R) with
+ *       R^2 >= max_i (r_i + D_i)^2 + D_i^2/32 + 2^-12 (|c_i|^2 + r_i^2) + 1e-4 r_i + 1e-10,
+ *       and the cluster pass uses the origin term q(1-kappa)(1-2^-12): the ordinary filter rules a
+ *       sphere out only if dist^2 > R^2 (its own rounding is inside kappa), the extra 2^-12 |o|^2
+ *       covers the |o|^2 share of 33 eta_i = 2112u (...) < 2^-12 (...).
+ * Candidates then reach the exact expressions in cluster order, so the resolve steps break
+ * ties by sphere index explicitly (first index wins, raytracer.h:166-188 / :264).
+ */
+#define RT_CLUSTER 8
+#define RT_KAPPA2 2.44140625e-04f     /* 2^-12 */
+
 struct OriginQ { float px, py, pz, nq; };    /* -2o, -|o|^2(1-kappa) (never -0) */
 struct DirQ { float ndx, ndy, ndz, od; };    /* -d', d'.o   (d' = d/|d|)       */
 
@@ -159,6 +185,13 @@ RT_HD bool make_dir(DirQ& D, V3 o, V3 d) {
   D.ndx = -ux; D.ndy = -uy; D.ndz = -uz;
   D.od = fast_fma(uz, o.z, fast_fma(uy, o.y, ex_mul(ux, o.x)));
   return true;
+}
+
+/* origin term of the cluster pass: q(1-kappa)(1-2^-12), see "Cluster filter" */
+RT_HD OriginQ cluster_origin(const OriginQ& O) {
+  OriginQ C = O;
+  C.nq = ex_mul(O.nq, 1.f - RT_KAPPA2);
+  return C;
 }
 
 RT_HD float filter_ch(const OriginQ& O, float4_ s) {

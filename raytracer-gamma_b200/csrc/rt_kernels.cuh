@@ -37,6 +37,7 @@ namespace rtg {
 #define RT_BLOCK 256
 #endif
 #define RT_LIST_MAX 24
+#define RT_LIST1_MAX 40      /* accelerated mode: (sub, cluster) entries per lane between two flushes */
 #define RT_CONST_MAX_SPHERES 1024
 #define RT_NUM_COUNTERS 24
 #define RT_NO_PIXEL 0xFFFFFFFFu
@@ -119,7 +120,10 @@ struct WarpCtx {
   long long t0;
   long long phase[6];       /* refill+vote, set-up, filter loop, resolve, advance, (spare) */
 #endif
-  const float4* filt;       /* filter records (shared memory, or unused with __constant__) */
+  const float4* filt;       /* filter records (shared memory, or unused with __constant__); accelerated mode: cluster records */
+  const float4* mfilt;      /* accelerated mode: the clusters' member records (shared memory) */
+  const unsigned short* midx;   /* accelerated mode: the members' sphere indices (shared memory) */
+  unsigned short* list1;    /* accelerated mode: per-lane (sub, cluster) lists: list1[k * RT_BLOCK + tid] */
   unsigned short* list;     /* per-lane candidate lists: list[k * RT_BLOCK + tid]          */
   float* geo;               /* per-lane shadow-batch rays of the current pass: geo[w * RT_BLOCK + tid], 16 words */
   uint32_t tid;
@@ -505,6 +509,348 @@ __device__ __forceinline__ void pass_contain(const TraceParams& p, WarpCtx& w, S
   if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
 }
 
+/* ======================================================================================
+ * Accelerated mode (optional; "Cluster filter" in rt_core.cuh).  Each pass runs the SAME packed
+ * loop over the clusters' bounding records (an eighth of the sphere count), collects the
+ * (sub-query, cluster) pairs it cannot rule out, tests those clusters' members with the
+ * ordinary per-sphere filter and resolves the surviving spheres exactly.  The lists are
+ * flushed whenever a lane's list could overflow, so no input makes this mode fall back to
+ * the all-spheres resolve except what the brute-force mode also sends there.
+ * ====================================================================================== */
+template <int ND, int G>
+__device__ __forceinline__ void gather1(const WarpCtx& w, unsigned comb, uint32_t base, int& cnt) {
+  while (comb) {                      /* the caller made sure the list has room */
+    const int b = 31 - __clz(comb);
+    comb &= ~(1u << b);
+    const uint32_t idx = (uint32_t)(G * ND - 1 - b);
+    w.list1[cnt * RT_BLOCK + w.tid] = (unsigned short)(((idx % ND) << 14) | (base + idx / ND));
+    ++cnt;
+  }
+}
+
+/* members of cluster `cl` the per-sphere filter cannot rule out for one query (bit 7-m = member m) */
+template <bool HAS_DIR>
+__device__ __forceinline__ unsigned member_bits(const WarpCtx& w, uint32_t cl, const OriginQ& O, const DirQ& D) {
+  unsigned bits = 0u;
+#pragma unroll
+  for (int m = 0; m < RT_CLUSTER; ++m) {
+    const float4 v = w.mfilt[cl * RT_CLUSTER + m];
+    float4_ s; s.x = v.x; s.y = v.y; s.z = v.z; s.w = v.w;
+    const float ch = filter_ch(O, s);
+    const float d = HAS_DIR ? filter_ray(O, D, ch, s) : filter_point(O, ch);
+    bits = __funnelshift_l(__float_as_uint(d), bits, 1);
+  }
+  return ~bits & ((1u << RT_CLUSTER) - 1u);
+}
+/* append the flagged members of one cluster to the sphere list */
+__device__ __forceinline__ void gather2(const WarpCtx& w, unsigned bits, uint32_t cl, uint32_t sub, int& cnt2,
+                                        bool& overflow) {
+  while (bits) {
+    const int b = 31 - __clz(bits);
+    bits &= ~(1u << b);
+    if (cnt2 < RT_LIST_MAX) {
+      w.list[cnt2 * RT_BLOCK + w.tid] =
+          (unsigned short)((sub << 14) | w.midx[cl * RT_CLUSTER + (uint32_t)(RT_CLUSTER - 1 - b)]);
+      ++cnt2;
+    } else {
+      overflow = true;
+    }
+  }
+}
+
+template <bool USE_CONST>
+__device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+                                                 int s1, Counters& ctr) {
+  constexpr int G = RT_GROUP_T;
+  OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
+  DirQ D0, D1;
+  D0.ndx = D0.ndy = D0.ndz = D0.od = 0.f; D1 = D0;
+  bool live0 = false, live1 = false, exact0 = false, exact1 = false;
+  if (s0 >= 0) {
+    O0 = make_origin(slots[s0].qo);
+    live0 = make_dir(D0, slots[s0].qo, slots[s0].rayD);
+    exact0 = live0 && (p.noFilter || !(origin_filterable(O0) && dir_filterable(D0)));
+  }
+  if (s1 >= 0) {
+    O1 = make_origin(slots[s1].qo);
+    live1 = make_dir(D1, slots[s1].qo, slots[s1].rayD);
+    exact1 = live1 && (p.noFilter || !(origin_filterable(O1) && dir_filterable(D1)));
+  }
+  constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
+  const unsigned msk = pin(((live0 && !exact0) ? m0 : 0u) | ((live1 && !exact1) ? m1 : 0u));
+  const Origin2 OO = pack_origin(cluster_origin(O0), cluster_origin(O1));
+  const Dir2 DD = pack_dir(D0, D1);
+  float t0 = 1000.f, t1 = 1000.f;
+  int h0 = -1, h1 = -1;
+  bool overflow = false;
+  RT_TICK(1);
+  const uint32_t nPad = pin(p.noFilter ? 0u : w.nPad);
+  uint32_t base = 0;
+  for (;;) {
+    int cnt = 0;
+    bool full = false;
+    for (; base < nPad; base += G) {
+      unsigned k = 0;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
+        const f32x2 b = bq2(DD, cx, cy, cz);
+        f32x2 ch = fma2(OO.px, cx, pk1(s.w));
+        ch = fma2(OO.py, cy, ch);
+        ch = fma2(OO.pz, cz, ch);
+        const f32x2 d = fma2(b, b, sub2(OO.nq, ch));
+        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
+      }
+      const unsigned comb = ~k & msk;
+      if (__any_sync(RT_FULL, cnt + __popc(comb) > RT_LIST1_MAX)) { full = true; break; }
+      if (comb) gather1<2, G>(w, comb, base, cnt);
+    }
+    RT_TICK(2);
+    /* members of the surviving clusters */
+    /* members of the surviving clusters */
+    int cnt2 = 0;
+    const int maxc = __reduce_max_sync(RT_FULL, cnt);
+#pragma unroll 1
+    for (int k = 0; k < maxc; ++k) {
+      if (k < cnt) {
+        const uint32_t e = w.list1[k * RT_BLOCK + w.tid];
+        const uint32_t cl = e & 0x3FFFu, sub = e >> 14;
+        OriginQ O = O0; DirQ D = D0;
+        if (sub) { O = O1; D = D1; }
+        gather2(w, member_bits<true>(w, cl, O, D), cl, sub, cnt2, overflow);
+      }
+    }
+    const int maxc2 = __reduce_max_sync(RT_FULL, cnt2);
+#pragma unroll 1
+    for (int k = 0; k < maxc2; ++k) {
+      if (k < cnt2 && !overflow) {
+        const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+        const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+        if (i < p.sc.n) {
+          ctr.exactTests++;
+          const Slot& q = slots[sub ? s1 : s0];
+          const float t = ray_sphere_t(p.sc.geo[i], q.qo, q.rayD);
+          if (t > 0.f) {       /* raytracer.h:166-188: closest hit, the first index wins ties */
+            if (sub) { if (t < t1 || (t == t1 && (int)i < h1)) { t1 = t; h1 = (int)i; } }
+            else     { if (t < t0 || (t == t0 && (int)i < h0)) { t0 = t; h0 = (int)i; } }
+          }
+        }
+      }
+    }
+    RT_TICK(3);
+    if (!full) break;
+  }
+  if (overflow) { exact0 = live0; exact1 = live1; }
+  if (s0 >= 0) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
+  if (s1 >= 0) { slots[s1].minT = t1; slots[s1].hitIdx = h1; }
+  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
+  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+}
+
+template <bool USE_CONST, int ND>
+__device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+                                                  Counters& ctr) {
+  constexpr int G = (ND == 4) ? RT_GROUP_S4 : RT_GROUP_S2;
+  OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
+  DirQ D[ND];
+  unsigned live = 0u, exact = 0u;
+  bool asTrace = false;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; }
+  if (s0 >= 0) {
+    asTrace = slots[s0].kind == K_TRACE;
+    ShadowGeo g;
+    V3 org;
+    if (asTrace) {
+      org = slots[s0].qo;
+      g.d[0] = slots[s0].rayD; g.gap[0] = 0.f;
+#pragma unroll
+      for (int k = 1; k < RT_SHADOW_BATCH; ++k) { g.d[k] = mk(0.f, 0.f, 0.f); g.gap[k] = 0.f; }
+    } else {
+      org = slots[s0].P;
+      shadow_geo(slots[s0], p.sc, g);
+    }
+#pragma unroll
+    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+      w.geo[(4 * k + 0) * RT_BLOCK + w.tid] = g.d[k].x;
+      w.geo[(4 * k + 1) * RT_BLOCK + w.tid] = g.d[k].y;
+      w.geo[(4 * k + 2) * RT_BLOCK + w.tid] = g.d[k].z;
+      w.geo[(4 * k + 3) * RT_BLOCK + w.tid] = g.gap[k];
+    }
+    O = make_origin(org);
+    const bool ofil = origin_filterable(O);
+    const int nd = slots[s0].ndirs;
+#pragma unroll
+    for (int k = 0; k < ND; ++k) {
+      if (k < nd && make_dir(D[k], org, g.d[k])) {
+        live |= 1u << k;
+        if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
+      }
+    }
+  }
+  unsigned msk = 0u;
+#pragma unroll
+  for (int k = 0; k < ND; ++k) msk |= (((live & ~exact) >> k) & 1u) ? mask_of_sub<ND, G>(k) : 0u;
+  msk = pin(msk);
+  Dir2 DP[ND / 2];
+#pragma unroll
+  for (int k = 0; k < ND / 2; ++k) DP[k] = pack_dir(D[2 * k], D[2 * k + 1]);
+  const OriginQ OC = cluster_origin(O);
+  unsigned blocked = 0u;
+  float t0 = 1000.f;
+  int h0 = -1;
+  bool overflow = false;
+  RT_TICK(1);
+  const uint32_t nPad = pin(p.noFilter ? 0u : w.nPad);
+  uint32_t base = 0;
+  for (;;) {
+    int cnt = 0;
+    bool full = false;
+    for (; base < nPad; base += G) {
+      unsigned sk = 0u;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
+        const f32x2 e = pk1(ex_sub(OC.nq, filter_ch(OC, s)));
+#pragma unroll
+        for (int k = 0; k < ND / 2; ++k) {
+          const f32x2 b = bq2(DP[k], cx, cy, cz);
+          const f32x2 d = fma2(b, b, e);
+          sk = __funnelshift_l(__float_as_uint(lo_of(d)), sk, 1);
+          sk = __funnelshift_l(__float_as_uint(hi_of(d)), sk, 1);
+        }
+      }
+      const unsigned comb = ~sk & msk;
+      if (__any_sync(RT_FULL, cnt + __popc(comb) > RT_LIST1_MAX)) { full = true; break; }
+      if (comb) gather1<ND, G>(w, comb, base, cnt);
+    }
+    RT_TICK(2);
+    int cnt2 = 0;
+    const int maxc = __reduce_max_sync(RT_FULL, cnt);
+#pragma unroll 1
+    for (int k = 0; k < maxc; ++k) {
+      if (k < cnt) {
+        const uint32_t e = w.list1[k * RT_BLOCK + w.tid];
+        const uint32_t cl = e & 0x3FFFu, sub = e >> 14;
+        DirQ Ds = D[0];
+#pragma unroll
+        for (int j = 1; j < ND; ++j) if (sub == (uint32_t)j) Ds = D[j];
+        gather2(w, member_bits<true>(w, cl, O, Ds), cl, sub, cnt2, overflow);
+      }
+    }
+    const int maxc2 = __reduce_max_sync(RT_FULL, cnt2);
+#pragma unroll 1
+    for (int k = 0; k < maxc2; ++k) {
+      if (k < cnt2 && !overflow) {
+        const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+        const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+        if (i < p.sc.n && !((blocked >> sub) & 1u)) {
+          ctr.exactTests++;
+          const V3 d = mk(w.geo[(4 * sub + 0) * RT_BLOCK + w.tid], w.geo[(4 * sub + 1) * RT_BLOCK + w.tid],
+                          w.geo[(4 * sub + 2) * RT_BLOCK + w.tid]);
+          const V3 org = asTrace ? slots[s0].qo : slots[s0].P;
+          const float t = ray_sphere_t(p.sc.geo[i], org, d);
+          if (t > 0.f) {
+            if (asTrace) {
+              if (t < t0 || (t == t0 && (int)i < h0)) { t0 = t; h0 = (int)i; }
+            } else if (t < 1000.f) {
+              const V3 dist = vscale(t, d);
+              if (vdot(dist, dist) < w.geo[(4 * sub + 3) * RT_BLOCK + w.tid]) blocked |= 1u << sub;
+            }
+          }
+        }
+      }
+    }
+    RT_TICK(3);
+    if (!full) break;
+  }
+  if (overflow) exact = live;
+  if (s0 >= 0) {
+    if (asTrace) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
+    else slots[s0].blocked = blocked;
+  }
+  if (exact) ctr.exactTests += exact_all(p.sc, &slots[s0], exact);
+}
+
+template <bool USE_CONST>
+__device__ __forceinline__ void pass_contain_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+                                                   int s1, Counters& ctr) {
+  constexpr int G = RT_GROUP_C;
+  OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
+  bool exact0 = false, exact1 = false;
+  if (s0 >= 0) { O0 = make_origin(slots[s0].qo); exact0 = p.noFilter || !origin_filterable(O0); }
+  if (s1 >= 0) { O1 = make_origin(slots[s1].qo); exact1 = p.noFilter || !origin_filterable(O1); }
+  constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
+  const unsigned msk = pin(((s0 >= 0 && !exact0) ? m0 : 0u) | ((s1 >= 0 && !exact1) ? m1 : 0u));
+  const Origin2 OO = pack_origin(cluster_origin(O0), cluster_origin(O1));
+  int h0 = -1, h1 = -1;
+  bool overflow = false;
+  RT_TICK(1);
+  const uint32_t nPad = pin(p.noFilter ? 0u : w.nPad);
+  uint32_t base = 0;
+  DirQ none;
+  none.ndx = none.ndy = none.ndz = none.od = 0.f;
+  for (;;) {
+    int cnt = 0;
+    bool full = false;
+    for (; base < nPad; base += G) {
+      unsigned k = 0;
+#pragma unroll
+      for (int j = 0; j < G; ++j) {
+        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
+        ch = fma2(OO.py, pk1(s.y), ch);
+        ch = fma2(OO.pz, pk1(s.z), ch);
+        const f32x2 d = sub2(OO.nq, ch);
+        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
+      }
+      const unsigned comb = ~k & msk;
+      if (__any_sync(RT_FULL, cnt + __popc(comb) > RT_LIST1_MAX)) { full = true; break; }
+      if (comb) gather1<2, G>(w, comb, base, cnt);
+    }
+    RT_TICK(2);
+    int cnt2 = 0;
+    const int maxc = __reduce_max_sync(RT_FULL, cnt);
+#pragma unroll 1
+    for (int k = 0; k < maxc; ++k) {
+      if (k < cnt) {
+        const uint32_t e = w.list1[k * RT_BLOCK + w.tid];
+        const uint32_t cl = e & 0x3FFFu, sub = e >> 14;
+        OriginQ O = O0;
+        if (sub) O = O1;
+        gather2(w, member_bits<false>(w, cl, O, none), cl, sub, cnt2, overflow);
+      }
+    }
+    const int maxc2 = __reduce_max_sync(RT_FULL, cnt2);
+#pragma unroll 1
+    for (int k = 0; k < maxc2; ++k) {
+      if (k < cnt2 && !overflow) {
+        const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+        const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+        if (i < p.sc.n) {
+          ctr.exactTests++;
+          const bool in = contains_exact(p.sc.geo[i], slots[sub ? s1 : s0].qo);
+          if (in) {            /* raytracer.h:264: the first container in index order wins */
+            if (sub) { if (h1 < 0 || (int)i < h1) h1 = (int)i; }
+            else     { if (h0 < 0 || (int)i < h0) h0 = (int)i; }
+          }
+        }
+      }
+    }
+    RT_TICK(3);
+    if (!full) break;
+  }
+  if (overflow) { exact0 = s0 >= 0; exact1 = s1 >= 0; }
+  if (s0 >= 0) slots[s0].hitIdx = h0;
+  if (s1 >= 0) slots[s1].hitIdx = h1;
+  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
+  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+}
+
 /* Pull the state words of a slot that is about to be served into L1 while the sphere loop
  * runs: the per-lane slots live in local memory (one 128-byte line per word per warp), far
  * more than L1 holds across all resident warps, so without this the O(1) code after the loop
@@ -544,13 +890,15 @@ __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, Slot* slo
   return (uint32_t)s.kind | ((uint32_t)s.ndirs << 4);
 }
 
-template <bool USE_CONST, int MIN_BLOCKS, int NSLOTS>
+template <bool USE_CONST, int MIN_BLOCKS, int NSLOTS, bool ACCEL = false>
 __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const TraceParams p) {
+  static_assert(!(ACCEL && USE_CONST), "the accelerated mode stages its records in shared memory");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists][shadow-ray scratch] */
+  /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists][shadow-ray scratch];
+   * accelerated mode: [mbarrier][cluster records | member records | member indices][list1][list][scratch] */
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float4* sFilt = reinterpret_cast<float4*>(smem_raw + 16);
-  const uint32_t filtBytes = USE_CONST ? 0u : p.sc.nPad * 16u;
+  const uint32_t filtBytes = USE_CONST ? 0u : ACCEL ? p.sc.ncPad * (16u + RT_CLUSTER * 18u) : p.sc.nPad * 16u;
 
   const uint32_t tid = threadIdx.x, lane = tid & 31u;
 
@@ -562,7 +910,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
     __syncthreads();
     if (tid == 0 && filtBytes) {
       mbar_expect_tx(bar, filtBytes);
-      const unsigned char* src = reinterpret_cast<const unsigned char*>(p.sc.filt);
+      const unsigned char* src = reinterpret_cast<const unsigned char*>(ACCEL ? p.sc.cfilt : p.sc.filt);
       unsigned char* dstp = reinterpret_cast<unsigned char*>(sFilt);
       for (uint32_t off = 0; off < filtBytes; off += 32768u) {
         const uint32_t n = (filtBytes - off < 32768u) ? (filtBytes - off) : 32768u;
@@ -574,10 +922,14 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
 
   WarpCtx w;
   w.filt = sFilt;
-  w.list = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
-  w.geo = reinterpret_cast<float*>(smem_raw + 16 + filtBytes + RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short));
+  w.mfilt = sFilt + p.sc.ncPad;
+  w.midx = reinterpret_cast<const unsigned short*>(sFilt + (size_t)p.sc.ncPad * (1u + RT_CLUSTER));
+  const uint32_t list1Bytes = ACCEL ? RT_LIST1_MAX * RT_BLOCK * (uint32_t)sizeof(unsigned short) : 0u;
+  w.list1 = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
+  w.list = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes + list1Bytes);
+  w.geo = reinterpret_cast<float*>(smem_raw + 16 + filtBytes + list1Bytes + RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short));
   w.tid = tid;
-  w.nPad = p.sc.nPad;
+  w.nPad = ACCEL ? p.sc.ncPad : p.sc.nPad;
 #ifdef RT_PHASE_TIMING
   w.t0 = clock64();
   for (int i = 0; i < 6; ++i) w.phase[i] = 0;
@@ -664,14 +1016,19 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
       if (sv1 >= 0) prefetch_slot(slots[sv1]);
     }
     if (mode == K_SHADOW) {
-      if (ndMax <= 2) { pass_shadow<USE_CONST, 2>(p, w, slots, sv0, ctr); passS2++; }
-      else            { pass_shadow<USE_CONST, 4>(p, w, slots, sv0, ctr); passS4++; }
+      if (ndMax <= 2) {
+        if (ACCEL) pass_shadow_accel<USE_CONST, 2>(p, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 2>(p, w, slots, sv0, ctr);
+        passS2++;
+      } else {
+        if (ACCEL) pass_shadow_accel<USE_CONST, 4>(p, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 4>(p, w, slots, sv0, ctr);
+        passS4++;
+      }
       if (s0 >= 0) servedS += (unsigned)nd; else servedT += (unsigned)ndS;
     } else if (mode == K_TRACE) {
-      pass_trace<USE_CONST>(p, w, slots, t0, t1, ctr);
+      if (ACCEL) pass_trace_accel<USE_CONST>(p, w, slots, t0, t1, ctr); else pass_trace<USE_CONST>(p, w, slots, t0, t1, ctr);
       passT++; servedT += (unsigned)((t0 >= 0) + (t1 >= 0));
     } else {
-      pass_contain<USE_CONST>(p, w, slots, c0, c1, ctr);
+      if (ACCEL) pass_contain_accel<USE_CONST>(p, w, slots, c0, c1, ctr); else pass_contain<USE_CONST>(p, w, slots, c0, c1, ctr);
       passC++; servedC += (unsigned)((c0 >= 0) + (c1 >= 0));
     }
     RT_TICK(3);

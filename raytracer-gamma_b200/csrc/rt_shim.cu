@@ -49,6 +49,8 @@ struct rt_cuda_ctx {
   /* options */
   int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0, slots = 0, prefetch = 0;
   int engine = 0;                  /* 0 auto, 1 persistent kernel, 2 wavefront */
+  int accel = 0;                   /* 1: two-level cluster filter (optional accelerated mode) */
+  uint32_t nc = 0, ncPad = 0;
   long pool = 0;                   /* wavefront: samples in flight (0 = default) */
 
   /* wavefront pool */
@@ -176,6 +178,7 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!ctx || !key) return RT_CUDA_ERR_INVALID_ARG;
   if (!strcmp(key, "staging")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->staging = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
+  if (!strcmp(key, "accel")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->accel = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "engine")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->engine = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "pool")) { if (value < 0) return RT_CUDA_ERR_INVALID_ARG; ctx->pool = value; return RT_CUDA_OK; }
   if (!strcmp(key, "prefetch")) { ctx->prefetch = value ? 1 : 0; return RT_CUDA_OK; }
@@ -208,7 +211,7 @@ extern "C" int rt_cuda_upload_scene(rt_cuda_ctx* ctx, const rt_sphere* spheres, 
   CU(cudaStreamSynchronize(ctx->stream));   /* h goes out of scope */
 
   ctx->view = scene_view(ctx->dScene, lay);
-  ctx->n = lay.n; ctx->nPad = lay.nPad; ctx->nl = lay.nl;
+  ctx->n = lay.n; ctx->nPad = lay.nPad; ctx->nl = lay.nl; ctx->nc = lay.nc; ctx->ncPad = lay.ncPad;
   ctx->haveScene = true;
   return RT_CUDA_OK;
 }
@@ -223,6 +226,7 @@ static int ensure_frame(rt_cuda_ctx* ctx, size_t pixels) {
   return RT_CUDA_OK;
 }
 
+#define RT_ACCEL_MIN_SPHERES 512u           /* accel = 1 engages from here (slower below, scripts/quick_perf.py); accel = 2 forces it */
 #define RT_DEFAULT_POOL (1l << 21)          /* samples in flight of the wavefront engine */
 
 /* The wavefront engine: alternate the pure filter kernels and the shade kernel over a pool
@@ -397,8 +401,13 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   int staging = ctx->staging;
   if (staging == 0) staging = (ctx->n > 0 && ctx->nPad <= 64) ? 1 : 2;
   if (staging == 1 && (ctx->n == 0 || ctx->nPad > RT_CONST_MAX_SPHERES)) staging = 2;
+  /* the accelerated mode needs something to cull and its records in shared memory */
+  const bool accel = ctx->accel && !ctx->noFilter && ctx->n >= (ctx->accel == 2 ? 4u * RT_CLUSTER : RT_ACCEL_MIN_SPHERES);
+  if (accel) staging = 2;
   const bool useConst = (staging == 1);
-  const size_t smem = 16 + (useConst ? 0 : (size_t)ctx->nPad * 16) + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
+  const size_t sceneBytes = useConst ? 0 : accel ? (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) : (size_t)ctx->nPad * 16;
+  const size_t smem = 16 + sceneBytes + (accel ? (size_t)RT_LIST1_MAX * RT_BLOCK * sizeof(unsigned short) : 0)
+                      + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
                       + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
   /* variants: MIN_BLOCKS resident CTAs per SM (register budget), NSLOTS pixels in flight per lane */
   const int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
@@ -408,6 +417,9 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if (useConst) kern = (minBlocks == 2) ? RT_PICK(true, 2) : (minBlocks == 3) ? RT_PICK(true, 3) : RT_PICK(true, 4);
   else          kern = (minBlocks == 2) ? RT_PICK(false, 2) : (minBlocks == 3) ? RT_PICK(false, 3) : RT_PICK(false, 4);
 #undef RT_PICK
+  if (accel) kern = trace_kernel<false, RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS, true>;
+  ctx->stats.accel = accel ? 1u : 0u;
+  ctx->stats.clusters = accel ? ctx->nc : 0u;
   CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   int perSM = 0;
   CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, RT_BLOCK, smem));
@@ -559,7 +571,7 @@ extern "C" int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out) {
   s.served_trace = c[7]; s.served_shadow = c[8]; s.served_contain = c[9]; s.passes = c[11];
   s.passes_trace = c[12]; s.passes_shadow2 = c[13]; s.passes_shadow4 = c[14]; s.passes_contain = c[15];
   for (int i = 0; i < 6; ++i) s.phase_cycles[i] = c[16 + i];
-  s.filter_tests = ctx->noFilter ? 0 : c[10] * (unsigned long long)ctx->nPad;
+  s.filter_tests = ctx->noFilter ? 0 : c[10] * (unsigned long long)(s.accel ? ctx->ncPad : ctx->nPad);   /* accelerated mode: cluster tests only */
   s.sph_num = ctx->n; s.sph_padded = ctx->nPad; s.lgt_num = ctx->nl;
   s.width = ctx->W; s.height = ctx->H; s.local_rows = ctx->localRows;
   s.kernel_ms = 0.f;

@@ -55,19 +55,19 @@ def hostsim():
     lib.hostsim_render.restype = ctypes.c_int
 
     def render(spheres, lights, width, height, zoom=-4.0, alias=1.0, max_stack=6, rows=None,
-               no_filter=False):
+               no_filter=False, mode=None):
         begin, count, step = (0, height, 1) if rows is None else rows
         out = np.zeros((count, width, 3), np.float32)
-        ctr = (ctypes.c_uint64 * 8)()
+        ctr = (ctypes.c_uint64 * 10)()
         spheres = np.ascontiguousarray(spheres)
         lights = np.ascontiguousarray(lights)
         rc = lib.hostsim_render(spheres.ctypes.data if len(spheres) else None, len(spheres),
                                 lights.ctypes.data if len(lights) else None, len(lights),
                                 width, height, zoom, alias, max_stack, begin, count, step,
-                                out.ctypes.data, ctypes.addressof(ctr), int(no_filter))
+                                out.ctypes.data, ctypes.addressof(ctr), int(no_filter) if mode is None else int(mode))
         assert rc == 0
         names = ["rays", "shadow_rays", "contain_queries", "contain_tests", "exact_tests", "samples",
-                 "lane_iters", "active_lane_iters"]
+                 "lane_iters", "active_lane_iters", "accel_violations", "cluster_tests"]
         return out, dict(zip(names, [int(v) for v in ctr]))
 
     return render

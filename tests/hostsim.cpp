@@ -15,6 +15,77 @@
 
 using namespace rtg;
 
+/* The accelerated mode's answer (rt_kernels.cuh pass_*_accel): cluster records first, then the
+ * members of the clusters that were not ruled out, then the exact tests with explicit index
+ * tie-breaks.  With `audit` every sphere is ALSO tested exactly, and a sphere the exact test
+ * accepts inside a cluster the cluster filter ruled out counts as a violation (there must be none). */
+static void answer_accel(Slot& s, const SceneView& sc, Counters& ctr, ShadowGeo& sg, bool audit,
+                         const std::vector<uint32_t>& clusterOf, uint64_t& violations, uint64_t& clusterTests) {
+  const V3 org = (s.kind == K_SHADOW) ? s.P : s.qo;
+  const OriginQ O = make_origin(org);
+  const OriginQ OC = cluster_origin(O);
+  const bool ofil = origin_filterable(O);
+  std::vector<unsigned char> flagged(sc.nc);
+  auto brute = [&](auto&& fn) { for (uint32_t i = 0; i < sc.n; ++i) fn(i); };
+  auto culled = [&](const DirQ* D, auto&& fn) {
+    for (uint32_t c = 0; c < sc.nc; ++c) {
+      const float ch = filter_ch(OC, sc.cfilt[c]);
+      const float v = D ? filter_ray(OC, *D, ch, sc.cfilt[c]) : filter_point(OC, ch);
+      flagged[c] = !(v < 0.f);
+      ++clusterTests;
+      if (!flagged[c]) continue;
+      for (uint32_t m = 0; m < RT_CLUSTER; ++m) {
+        const float4_ rec = sc.mfilt[c * RT_CLUSTER + m];
+        const float chm = filter_ch(O, rec);
+        const float vm = D ? filter_ray(O, *D, chm, rec) : filter_point(O, chm);
+        if (vm < 0.f) continue;
+        const uint32_t i = sc.midx[c * RT_CLUSTER + m];
+        if (i < sc.n) fn(i);
+      }
+    }
+  };
+  if (s.kind == K_TRACE) {
+    DirQ D;
+    s.minT = 1000.f; s.hitIdx = -1;
+    if (!make_dir(D, s.qo, s.rayD)) return;
+    auto test = [&](uint32_t i) {
+      ctr.exactTests++;
+      float t;
+      if (ray_sphere_exact(sc.geo[i], s.qo, s.rayD, t) && (t < s.minT || (t == s.minT && (int)i < s.hitIdx))) { s.minT = t; s.hitIdx = (int)i; }
+    };
+    if (ofil && dir_filterable(D)) {
+      culled(&D, test);
+      if (audit) for (uint32_t i = 0; i < sc.n; ++i) { float t; if (ray_sphere_exact(sc.geo[i], s.qo, s.rayD, t) && !flagged[clusterOf[i]]) ++violations; }
+    } else brute(test);
+  } else if (s.kind == K_SHADOW) {
+    s.blocked = 0u;
+    shadow_geo(s, sc, sg);
+    for (int k = 0; k < s.ndirs; ++k) {
+      DirQ D;
+      if (!make_dir(D, org, sg.d[k])) continue;
+      auto test = [&](uint32_t i) {
+        if ((s.blocked >> k) & 1u) return;
+        ctr.exactTests++;
+        if (resolve_shadow(org, sg.d[k], sg.gap[k], sc.geo[i])) s.blocked |= 1u << k;
+      };
+      if (ofil && dir_filterable(D)) {
+        culled(&D, test);
+        if (audit) for (uint32_t i = 0; i < sc.n; ++i) { float t; if (ray_sphere_exact(sc.geo[i], org, sg.d[k], t) && !flagged[clusterOf[i]]) ++violations; }
+      } else brute(test);
+    }
+  } else if (s.kind == K_CONTAIN) {
+    s.hitIdx = -1;
+    auto test = [&](uint32_t i) {
+      ctr.exactTests++;
+      if (contains_exact(sc.geo[i], s.qo) && (s.hitIdx < 0 || (int)i < s.hitIdx)) s.hitIdx = (int)i;
+    };
+    if (ofil) {
+      culled(nullptr, test);
+      if (audit) for (uint32_t i = 0; i < sc.n; ++i) if (contains_exact(sc.geo[i], s.qo) && !flagged[clusterOf[i]]) ++violations;
+    } else brute(test);
+  }
+}
+
 /* Answer the slot's pending query the way one pass of the kernel does. */
 static void answer(Slot& s, const SceneView& sc, Counters& ctr, bool noFilter, ShadowGeo& sg) {
   const V3 org = (s.kind == K_SHADOW) ? s.P : s.qo;
@@ -61,7 +132,7 @@ static void answer(Slot& s, const SceneView& sc, Counters& ctr, bool noFilter, S
 extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_light* lights,
                               unsigned nl, unsigned W, unsigned H, float zoom, float alias, int S,
                               unsigned row_begin, unsigned row_count, unsigned row_step,
-                              float* out, uint64_t* counters /* [8] or NULL */, int noFilter) {
+                              float* out, uint64_t* counters /* [10] or NULL */, int mode /* 0 filter, 1 exact only, 2 accelerated, 3 accelerated + audit */) {
   if (!out || W == 0 || H == 0 || S < 1 || S > RT_MAX_STACK) return -1;
   if (row_step == 0) row_step = 1;
   std::vector<float4_> h;
@@ -69,9 +140,12 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
   build_scene_soa(spheres, n, lights, nl, h, lay);
   const SceneView sc = scene_view(h.data(), lay);
   const Camera cam = make_camera(W, H, zoom, alias, S, (int)sc.n);
-  uint64_t c[8] = {0, 0, 0, 0, 0, 0, 0, 0};
+  uint64_t c[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0};
+  std::vector<uint32_t> clusterOf(sc.n, 0u);
+  for (uint32_t k = 0; k < sc.nc * RT_CLUSTER; ++k)
+    if (sc.midx[k] < sc.n) clusterOf[sc.midx[k]] = k / RT_CLUSTER;
 
-#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c[:8])
+#pragma omp parallel for schedule(dynamic, 1) reduction(+ : c[:10])
   for (long k = 0; k < (long)row_count; ++k) {
     const unsigned gy = row_begin + (unsigned)k * row_step;
     for (unsigned gx = 0; gx < W; ++gx) {
@@ -88,7 +162,8 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
           for (;;) {
             c[6]++; c[7]++;
             ShadowGeo sg;
-            answer(s, sc, ctr, noFilter != 0, sg);
+            if (mode >= 2) answer_accel(s, sc, ctr, sg, mode == 3, clusterOf, c[8], c[9]);
+            else answer(s, sc, ctr, mode == 1, sg);
             if (advance(s, stack, ctr, sc, cam, &sg)) break;
           }
           samples[count++] = sample_value(s, cam);

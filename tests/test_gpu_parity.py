@@ -121,7 +121,7 @@ def test_staging_and_filter_variants_agree(pkg, orc_mod, gpu):
     base, _, st0 = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8)
     for opts in ({"staging": 1}, {"staging": 2}, {"no_filter": 1}, {"blocks_per_sm": 1}, {"slots": 2}, {"slots": 3},
                  {"min_blocks": 3}, {"min_blocks": 4}, {"prefetch": 1}, {"engine": 1}, {"engine": 2},
-                 {"engine": 2, "pool": 777}, {"engine": 2, "no_filter": 1}):
+                 {"engine": 2, "pool": 777}, {"engine": 2, "no_filter": 1}, {"accel": 2}, {"accel": 2, "no_filter": 1}):
         fb, _, st = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8, **opts)
         assert np.array_equal(orc_mod.canon(fb), orc_mod.canon(base)), opts
         assert st["rays"] == st0["rays"]
@@ -155,6 +155,33 @@ def test_edge_cases(pkg, orc_mod, oracle, gpu):
     fresh.close()
 
 
+def test_accelerated_mode_matches_oracle(pkg, orc_mod, oracle, gpu):
+    """Option accel=1 (two-level cluster filter) changes which spheres are looked
+    at, never the answer: bit-exact frames and the reference's work counters, far fewer filter tests."""
+    for (sph, lgt), (W, H, alias, S) in [(pkg.synth_scene(300, 4, seed=4), (160, 90, 2.0, 8)),
+                                          (pkg.synth_scene(1024, 4), (192, 108, 1.0, 8)),
+                                          (pkg.synth_scene(64, 2, seed=8), (97, 61, 1.0, 5)),
+                                          (pkg.synth_scene(2500, 3, seed=2), (96, 54, 1.0, 6))]:
+        ref, ctr = oracle.render(sph, lgt, W, H, -4.0, alias, S)
+        fb0, _, st0 = _render(gpu, sph, lgt, W, H, -4.0, alias, S)
+        fb, mx, st = _render(gpu, sph, lgt, W, H, -4.0, alias, S, accel=2)
+        assert st["accel"] == 1 and st0["accel"] == 0 and st["clusters"] >= (len(sph) + 7) // 8
+        _assert_parity(orc_mod, oracle, ref, fb)
+        assert np.array_equal(orc_mod.canon(fb), orc_mod.canon(fb0))
+        for k in ("rays", "shadow_rays", "contain_queries", "contain_tests", "samples"):
+            assert st[k] == ctr[k], k
+        assert st["filter_tests"] * 3 < st0["filter_tests"]
+    # too few spheres to cull: the option is ignored
+    sph, lgt = pkg.default_scene()
+    _, _, st = _render(gpu, sph, lgt, 64, 48, -4.0, 1.0, 6, accel=2)
+    assert st["accel"] == 0
+    # accel=1 only engages where it pays (>= 512 spheres)
+    sph, lgt = pkg.synth_scene(300, 4, seed=4)
+    assert _render(gpu, sph, lgt, 64, 48, -4.0, 1.0, 6, accel=1)[2]["accel"] == 0
+    sph, lgt = pkg.synth_scene(600, 4, seed=4)
+    assert _render(gpu, sph, lgt, 64, 48, -4.0, 1.0, 6, accel=1)[2]["accel"] == 1
+
+
 @pytest.mark.parametrize("engine", [1, 2])
 def test_both_engines_match_oracle(pkg, orc_mod, oracle, gpu, engine):
     """The persistent kernel and the wavefront engine are two schedules of the same per-sample
@@ -182,10 +209,10 @@ def test_rare_paths(pkg, orc_mod, oracle, gpu):
     from test_hostsim import _stress_scenes
     for name, (sph, lgt) in _stress_scenes(pkg).items():
         ref, ctr = oracle.render(sph, lgt, 96, 64, -4.0, 1.0, 8)
-        for engine in (1, 2):
-            fb, mx, st = _render(gpu, sph, lgt, 96, 64, -4.0, 1.0, 8, engine=engine)
+        for opts in ({"engine": 1}, {"engine": 2}, {"accel": 2}):
+            fb, mx, st = _render(gpu, sph, lgt, 96, 64, -4.0, 1.0, 8, **opts)
             _assert_parity(orc_mod, oracle, ref, fb)
-            assert st["rays"] == ctr["rays"] and st["shadow_rays"] == ctr["shadow_rays"], (name, engine)
+            assert st["rays"] == ctr["rays"] and st["shadow_rays"] == ctr["shadow_rays"], (name, opts)
     sph, lgt = pkg.synth_scene(12288, 4, seed=2)          # RT_CUDA_MAX_SPHERES
     fb, mx, st = _render(gpu, sph, lgt, 48, 27, -4.0, 1.0, 8)
     ref, ctr = oracle.render(sph, lgt, 48, 27, -4.0, 1.0, 8)

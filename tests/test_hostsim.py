@@ -121,3 +121,38 @@ def test_machine_rare_paths(pkg, orc_mod, oracle, hostsim):
         b, cb = hostsim(sph, lgt, 64, 48, -4.0, 1.0, 8)
         assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), name
         assert ca["rays"] == cb["rays"] and ca["shadow_rays"] == cb["shadow_rays"], name
+
+
+def test_cluster_filter_is_conservative_and_exact(pkg, orc_mod, oracle, hostsim):
+    """Accelerated mode (two-level cluster filter): same pixels as the oracle, and an audit of EVERY
+    query finds no sphere the exact test accepts inside a cluster the cluster filter ruled out."""
+    for n, l, seed, W, H, alias, S in [(256, 4, 0, 96, 54, 2.0, 8), (1024, 4, 0, 64, 36, 1.0, 8),
+                                       (100, 3, 7, 64, 48, 1.0, 6), (37, 1, 9, 57, 33, 1.0, 4)]:
+        sph, lgt = pkg.synth_scene(n, l, seed=seed)
+        a, ca = oracle.render(sph, lgt, W, H, -4.0, alias, S)
+        b, cb = hostsim(sph, lgt, W, H, -4.0, alias, S, mode=3)
+        assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), (n, l, seed)
+        assert cb["accel_violations"] == 0
+        assert ca["rays"] == cb["rays"] and ca["shadow_rays"] == cb["shadow_rays"]
+        queries = cb["rays"] + cb["contain_queries"]
+        assert cb["cluster_tests"] <= queries * ((n + 7) // 8 + 1)      # an eighth of the brute-force filter tests
+
+
+def test_cluster_filter_rare_paths(pkg, orc_mod, oracle, hostsim):
+    """The stress scenes (nested / coincident / huge / tiny / non-finite spheres, light inside a sphere)
+    through the accelerated mode, audited."""
+    for name, (sph, lgt) in _stress_scenes(pkg).items():
+        a, ca = oracle.render(sph, lgt, 64, 48, -4.0, 1.0, 8)
+        b, cb = hostsim(sph, lgt, 64, 48, -4.0, 1.0, 8, mode=3)
+        assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), name
+        assert cb["accel_violations"] == 0, name
+    # far-away, large-coordinate scene: the slack terms scale with |o|^2 and |c|^2
+    sph, lgt = pkg.synth_scene(200, 2, seed=3)
+    far = sph.copy()
+    far["pos"] = far["pos"] * np.float32(37.0)
+    far["radius"] = far["radius"] * np.float32(37.0)
+    flt = lgt.copy()
+    flt["pos"] = flt["pos"] * np.float32(37.0)
+    a, _ = oracle.render(far, flt, 64, 48, -4.0, 1.0, 8)
+    b, cb = hostsim(far, flt, 64, 48, -4.0, 1.0, 8, mode=3)
+    assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)) and cb["accel_violations"] == 0
