@@ -61,6 +61,7 @@ def parse():
     ap.add_argument("--cpu-seconds", type=float, default=12.0, help="target CPU time of the baseline sample")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--no-accel", action="store_true", help="skip the optional accelerated-mode leg")
     ap.add_argument("--verify", action="store_true",
                     help="N>1: rank 0 also renders the whole frame alone and checks the assembled frame is byte-identical")
     return ap.parse_args()
@@ -403,6 +404,39 @@ def run_ours(args):
                        "rt_cuda_upload_scene -> rt_cuda_render_strips -> NCCL all-reduce(max) -> rt_cuda_quantise -> "
                        "NCCL all-gather -> rt_cuda_assemble_rgb8 -> D2H to pinned host on rank 0"}
 
+    # ---------------- optional accelerated mode: same workload, cluster filter on
+    accel = None
+    if not args.no_accel and nsph >= 512:
+        ka = max(1, min(3, args.steps))
+        with torch.cuda.stream(stream):
+            step_device()
+            stream.synchronize()
+            base_rgb = rgb_local.clone()
+            r.set_option("accel", 1)
+            step_device()
+            barrier()
+            eva = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(ka)]
+            for i in range(ka):
+                flush.fill_(i & 0xFF)
+                eva[i][0].record(stream)
+                step_device()
+                eva[i][1].record(stream)
+            barrier()
+            st_a = r.stats()
+            same = bool(torch.equal(base_rgb, rgb_local))
+            r.set_option("accel", 0)
+        ta = torch.tensor([sum(a.elapsed_time(b) for a, b in eva), st_a["kernel_ms"], 0.0 if same else 1.0],
+                          dtype=torch.float64, device=dev)
+        if G > 1:
+            dist.all_reduce(ta, op=dist.ReduceOp.MAX)
+        accel = {"value": rays * ka / (float(ta[0]) * 1e-3) / 1e6, "unit": "Mrays/s", "steps": ka,
+                 "ms_per_step": float(ta[0]) / ka, "trace_kernel_ms_max_over_ranks": float(ta[1]),
+                 "speedup_vs_default": ms_per_step / (float(ta[0]) / ka),
+                 "rgb8_identical_to_default": float(ta[2]) == 0.0,
+                 "clusters": st_a["clusters"], "filter_tests_rank0": st_a["filter_tests"], "exact_tests_rank0": st_a["exact_tests"],
+                 "note": "option accel=1: two-level cluster filter, bit-identical frame; not the headline "
+                         "(the roofline above is the brute-force kernel's)"}
+
     # ---------------- roofline of the dominant kernel (rank 0's trace kernel)
     roofline = cpu = parity = None
     if rank == 0:
@@ -486,6 +520,7 @@ def run_ours(args):
             "clocks": clocks.report(),
             "e2e": e2e, "gpu_launches": launches_per_step * args.steps,
             "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity,
+            "accelerated_mode": accel,
         }
         if identical is not None:
             line["multi_gpu_frame_identical_to_1gpu"] = identical

@@ -272,6 +272,15 @@ def test_host_program_writes_the_reference_ppm(pkg, tmp_path):
     assert hashlib.md5(out.read_bytes()).hexdigest() == FACTS["default_800x600_a3_s6"]["ppm_md5"]
     res = subprocess.run([str(pkg.HOST_BIN), "--list"], capture_output=True, text=True, timeout=60)
     assert res.returncode == 0 and "CUDA device" in res.stdout
+    # a synthetic scene with and without the optional accelerated mode: the same file
+    md5 = []
+    for extra in ([], ["--accel"]):
+        o = tmp_path / f"synth{len(extra)}.ppm"
+        res = subprocess.run([str(pkg.HOST_BIN), "--spheres", "700", "--width", "320", "--height", "180", "--alias", "2",
+                              "--depth", "8", "--out", str(o)] + extra, capture_output=True, text=True, timeout=300)
+        assert res.returncode == 0, res.stdout + res.stderr
+        md5.append(hashlib.md5(o.read_bytes()).hexdigest())
+    assert md5[0] == md5[1]
 
 
 def test_full_size_properties_config4(pkg, orc_mod, oracle, gpu):
@@ -289,5 +298,11 @@ def test_full_size_properties_config4(pkg, orc_mod, oracle, gpu):
     # shard 5 of 8 (16-row strips) is the same pixels as the corresponding rows of the full frame
     gpu.render_strips(W, H, -4.0, alias, S, 16, 5, 8)
     part, _ = gpu.readback()
+    gpu.set_option("accel", 1)
+    gpu.render_strips(W, H, -4.0, alias, S, 16, 5, 8)
+    part_accel, _ = gpu.readback()
+    assert gpu.stats()["accel"] == 1
+    gpu.set_option("accel", 0)
+    assert np.array_equal(orc_mod.canon(part_accel), orc_mod.canon(part))
     mine = pkg.local_rows(H, 16, 5, 8)
     assert np.array_equal(orc_mod.canon(part), orc_mod.canon(fb[mine]))
