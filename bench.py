@@ -406,7 +406,7 @@ def run_ours(args):
 
     # ---------------- optional accelerated mode: same workload, cluster filter on
     accel = None
-    if not args.no_accel and nsph >= 512:
+    if not args.no_accel and nsph >= 768:
         ka = max(1, min(3, args.steps))
         with torch.cuda.stream(stream):
             step_device()

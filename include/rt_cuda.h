@@ -129,7 +129,7 @@ int rt_cuda_synchronize(rt_cuda_ctx* ctx);
  * "slots" 0 auto | 2 | 3 | 4 = pixels in flight per lane;
  * "engine" 0 auto (= 1) | 1 persistent kernel | 2 wavefront (slower; kept as a measured alternative);
  * "pool" = wavefront samples in flight;
- * "accel" 0 off | 1 = two-level cluster filter where it pays (>= 512 spheres) | 2 = from 32 spheres.
+ * "accel" 0 off | 1 = two-level cluster filter where it pays (>= 768 spheres) | 2 = from 32 spheres.
  *   Same frame bit for bit; fewer filter tests.  Off by default: the reference's
  *   algorithm is brute force and the default kernel is measured against that roofline. */
 int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value);

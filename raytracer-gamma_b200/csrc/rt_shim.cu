@@ -226,7 +226,7 @@ static int ensure_frame(rt_cuda_ctx* ctx, size_t pixels) {
   return RT_CUDA_OK;
 }
 
-#define RT_ACCEL_MIN_SPHERES 512u           /* accel = 1 engages from here (slower below, scripts/quick_perf.py); accel = 2 forces it */
+#define RT_ACCEL_MIN_SPHERES 768u           /* accel = 1 engages from here (6 % slower at 512, 25 % faster at 1024: profiles/r1/sweep_config5.jsonl); accel = 2 forces it */
 #define RT_DEFAULT_POOL (1l << 21)          /* samples in flight of the wavefront engine */
 
 /* The wavefront engine: alternate the pure filter kernels and the shade kernel over a pool

@@ -44,7 +44,7 @@ int main(int argc, char** argv) {
   int depth = 6;                             /* raytraceStack.h:10 */
   unsigned nSpheres = 0, nLights = 4, frames = 1;
   unsigned long long seed = 0;
-  int device = 0, accel = 0;                 /* --accel: optional two-level cluster filter (same frame, faster from ~512 spheres) */
+  int device = 0, accel = 0;                 /* --accel: optional two-level cluster filter (same frame, faster from ~768 spheres) */
   std::string out = "testPPM.ppm";           /* main.cpp:501 */
   std::string sceneFile, saveScene;
 

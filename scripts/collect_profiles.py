@@ -45,7 +45,7 @@ agg = collections.defaultdict(lambda: [0, 0.0])
 for r in rows:
     k = r["Kernel Name"].split("(")[0]; agg[k][0] += 1; agg[k][1] += float(r["Metric Value"]) / 1e6
 tot = sum(v[1] for v in agg.values())
-lines = ["# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline` (cold-cache, serialised: compare shares)",
+lines = ["# ncu launch list of `python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-accel` (cold-cache, serialised: compare shares)",
          "", "kernel | launches | total ms | share", "---|---|---|---"]
 for k, v in sorted(agg.items(), key=lambda kv: -kv[1][1]):
     lines.append(f"{k} | {v[0]} | {v[1]:.3f} | {v[1] / tot * 100:.2f} %")

@@ -175,10 +175,10 @@ def test_accelerated_mode_matches_oracle(pkg, orc_mod, oracle, gpu):
     sph, lgt = pkg.default_scene()
     _, _, st = _render(gpu, sph, lgt, 64, 48, -4.0, 1.0, 6, accel=2)
     assert st["accel"] == 0
-    # accel=1 only engages where it pays (>= 512 spheres)
+    # accel=1 only engages where it pays (>= 768 spheres)
     sph, lgt = pkg.synth_scene(300, 4, seed=4)
     assert _render(gpu, sph, lgt, 64, 48, -4.0, 1.0, 6, accel=1)[2]["accel"] == 0
-    sph, lgt = pkg.synth_scene(600, 4, seed=4)
+    sph, lgt = pkg.synth_scene(800, 4, seed=4)
     assert _render(gpu, sph, lgt, 64, 48, -4.0, 1.0, 6, accel=1)[2]["accel"] == 1
 
 
@@ -276,7 +276,7 @@ def test_host_program_writes_the_reference_ppm(pkg, tmp_path):
     md5 = []
     for extra in ([], ["--accel"]):
         o = tmp_path / f"synth{len(extra)}.ppm"
-        res = subprocess.run([str(pkg.HOST_BIN), "--spheres", "700", "--width", "320", "--height", "180", "--alias", "2",
+        res = subprocess.run([str(pkg.HOST_BIN), "--spheres", "900", "--width", "320", "--height", "180", "--alias", "2",
                               "--depth", "8", "--out", str(o)] + extra, capture_output=True, text=True, timeout=300)
         assert res.returncode == 0, res.stdout + res.stderr
         md5.append(hashlib.md5(o.read_bytes()).hexdigest())
