@@ -1,24 +1,26 @@
 /* rt_kernels.cuh — sm_100a kernels of the trace loop.
  *
- * trace_kernel     persistent CTAs; every lane owns NSLOTS pixels in flight.  Replaces
+ * trace_kernel     persistent CTAs; every lane owns NSLOTS samples in flight.  Replaces
  *                  `__kernel raytrace` (raytrace_kernel.cl:870-973) and the CPU pixel
- *                  loop (main.cpp:404-453).
+ *                  loop (main.cpp:404-453).  ACCEL = the optional two-level cluster filter.
+ * combine_kernel   sums each pixel's samples in the reference's order, takes the frame maximum
  * pack_kernel      float4 framebuffer -> packed Vec[W*H] (the reference's dst layout)
  * quantise_kernel  float4 framebuffer + max -> RGB8 (main.cpp:71-76)
  * assemble_rgb8_kernel  multi-GPU strip de-interleave
  *
  * One pass of trace_kernel (per warp, all lanes converged throughout):
- *   refill   free slots take the next pixels from a tile queue (one global atomicAdd
+ *   refill   free slots take the next samples from a tile queue (one global atomicAdd
  *            per warp granule, __ballot_sync ranks the takers)
  *   vote     every lane reports which query kinds its slots are waiting on; the warp
  *            picks the kind that fills most lanes (__reduce_add_sync)
  *   filter   the chosen kind's loop over ALL spheres, sphere records staged once per
  *            CTA into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier) or
  *            read from __constant__ for small scenes:
- *              trace    2 rays per lane    (1 LDS.128 + 2 x [7 FFMA + FADD + SHF]) per sphere
- *              shadow   4 rays, one origin (1 LDS.128 + 3 FFMA + 4 x [4 FFMA + FADD + SHF])
- *              contain  2 probes per lane  (1 LDS.128 + 2 x [3 FFMA + FADD + SHF])
- *            each test leaves one SIGN BIT (certain miss or not) in a funnel-shifted mask
+ *              trace    2 rays per lane    (1 LDS.128 + 7 FFMA2 + FADD2 + 2 SHF) per sphere
+ *              shadow   4 rays, one origin (1 LDS.128 + 3 FFMA + FADD + 2 x [4 FFMA2 + 2 SHF])
+ *              contain  2 probes per lane  (1 LDS.128 + 3 FFMA2 + FADD2 + 2 SHF)
+ *            (packed FP32 pairs: one FFMA2 serves both rays) — each test leaves one SIGN BIT
+ *            (certain miss or not) in the group's funnel-shifted register
  *   gather   set bits become (sub-query, sphere) entries in a per-lane shared-memory list
  *   resolve  k-th entries of all lanes go through the reference's exact expressions together
  *   advance  the served slots take their O(1) shading / state transition (one kind per
