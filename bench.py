@@ -43,7 +43,7 @@ WORKLOADS = {
 ZOOM = -4.0
 FLOP_PER_TEST = 17.0      # hoisted ray-sphere discriminant
 FLOP_PER_CONTAIN = 8.0    # primaryContainer test
-STRIP_ROWS = 16
+STRIP_ROWS = 4        # one 8x4-tile row per strip: 4320 rows split evenly over 2, 4 and 8 ranks
 
 
 def parse():

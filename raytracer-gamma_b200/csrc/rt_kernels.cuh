@@ -120,7 +120,8 @@ __device__ __forceinline__ bool work_to_task(const TraceParams& p, uint32_t idx,
 struct WarpCtx {
 #ifdef RT_PHASE_TIMING
   long long t0;
-  long long phase[6];       /* refill+vote, set-up, filter loop, resolve, advance, (spare) */
+  long long phase[6];       /* tail (cycles after the queue ran dry), set-up, filter loop, resolve, advance, longest tail */
+  long long tDry;
 #endif
   const float4* filt;       /* filter records (shared memory, or unused with __constant__); accelerated mode: cluster records */
   const float4* mfilt;      /* accelerated mode: the clusters' member records (shared memory) */
@@ -933,7 +934,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
   w.tid = tid;
   w.nPad = ACCEL ? p.sc.ncPad : p.sc.nPad;
 #ifdef RT_PHASE_TIMING
-  w.t0 = clock64();
+  w.t0 = w.tDry = clock64();
   for (int i = 0; i < 6; ++i) w.phase[i] = 0;
 #endif
 
@@ -963,7 +964,13 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
           uint32_t b = 0;
           if (lane == 0) b = atomicAdd(p.workCounter, p.chunk);
           b = __shfl_sync(RT_FULL, b, 0);
-          if (b >= p.totalWork) { queueDry = true; break; }
+          if (b >= p.totalWork) {
+            queueDry = true;
+#ifdef RT_PHASE_TIMING
+            w.tDry = clock64();
+#endif
+            break;
+          }
           wbase = b;
           wend = (b + p.chunk < p.totalWork) ? b + p.chunk : p.totalWork;
         }
@@ -1057,7 +1064,11 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
 
 #ifdef RT_PHASE_TIMING
   if (lane == 0)
-    for (int i = 0; i < 6; ++i) atomicAdd(&p.counters[16 + i], (unsigned long long)w.phase[i]);
+  {
+    w.phase[0] = w.phase[5] = clock64() - w.tDry;
+    for (int i = 0; i < 5; ++i) atomicAdd(&p.counters[16 + i], (unsigned long long)w.phase[i]);
+    atomicMax(&p.counters[16 + 5], (unsigned long long)w.phase[5]);
+  }
 #endif
   /* ---- per-warp reductions ---- */
   unsigned mb = __float_as_uint(laneMax);   /* laneMax >= 0: uint order == float order */
