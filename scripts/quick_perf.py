@@ -21,7 +21,10 @@ cases = [
 ]
 if len(sys.argv) > 1:
     cases = [c for c in cases if any(a in c[0] for a in sys.argv[1:])]
+import os
+GLOBAL_OPTS = {kv.split("=")[0]: int(kv.split("=")[1]) for kv in os.environ.get("RTG_OPTS", "").split(",") if "=" in kv}
 for name, (sph, lgt), W, H, alias, S, opts in cases:
+    opts = {**GLOBAL_OPTS, **opts}
     for k, v in opts.items():
         r.set_option(k, v)
     r.upload_scene(sph, lgt)
