@@ -22,6 +22,7 @@ using namespace rtg;
 struct rt_cuda_ctx {
   int device = 0;
   int smCount = 0;
+  int smemOptin = 0;               /* largest dynamic shared memory one CTA may ask for */
   cudaStream_t stream = nullptr;
   bool ownStream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -130,6 +131,7 @@ extern "C" int rt_cuda_init(int device, rt_cuda_ctx** out) {
     return fail(RT_CUDA_ERR_NO_DEVICE);
   }
   ctx->smCount = pr.multiProcessorCount;
+  ctx->smemOptin = (int)pr.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(RT_CUDA_ERR_CUDA);
   ctx->ownStream = true;
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return fail(RT_CUDA_ERR_CUDA);
@@ -402,7 +404,11 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if (staging == 0) staging = (ctx->n > 0 && ctx->nPad <= 64) ? 1 : 2;
   if (staging == 1 && (ctx->n == 0 || ctx->nPad > RT_CONST_MAX_SPHERES)) staging = 2;
   /* the accelerated mode needs something to cull and its records in shared memory */
-  const bool accel = ctx->accel && !ctx->noFilter && ctx->n >= (ctx->accel == 2 ? 4u * RT_CLUSTER : RT_ACCEL_MIN_SPHERES);
+  const size_t perCta = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short) + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float) + 16;
+  const size_t accelBytes = (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) + (size_t)RT_LIST1_MAX * RT_BLOCK * sizeof(unsigned short);
+  /* ... and falls back to the plain mode when they do not fit one CTA (> ~8 000 spheres) */
+  const bool accel = ctx->accel && !ctx->noFilter && ctx->n >= (ctx->accel == 2 ? 4u * RT_CLUSTER : RT_ACCEL_MIN_SPHERES) &&
+                     perCta + accelBytes <= (size_t)ctx->smemOptin;
   if (accel) staging = 2;
   const bool useConst = (staging == 1);
   const size_t sceneBytes = useConst ? 0 : accel ? (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) : (size_t)ctx->nPad * 16;

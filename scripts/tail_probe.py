@@ -24,4 +24,4 @@ with pkg.Renderer(0) as r:
                           "ns_per_ray": round(best["kernel_ms"] * 1e6 / best["rays"], 4),
                           "fill": round(best["active_lane_iters"] / best["lane_iters"], 4), "rows": best["local_rows"],
                           "mean_tail_ms": round(best["phase_cycles"][0] / (best["grid"] * 8) / 1.965e6, 3),
-                          "max_tail_ms": round(best["phase_cycles"][5] / 1.965e6, 3)}))
+                          "max_tail_ms": round(best["phase_cycles"][5] / 1.965e6, 3)}), flush=True)

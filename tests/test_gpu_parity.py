@@ -218,6 +218,13 @@ def test_rare_paths(pkg, orc_mod, oracle, gpu):
     ref, ctr = oracle.render(sph, lgt, 48, 27, -4.0, 1.0, 8)
     _assert_parity(orc_mod, oracle, ref, fb)
     assert st["rays"] == ctr["rays"]
+    # the accelerated mode's records no longer fit one CTA at this size: the option falls back, it does not fail
+    fb2, _, st2 = _render(gpu, sph, lgt, 48, 27, -4.0, 1.0, 8, accel=1)
+    assert st2["accel"] == 0 and np.array_equal(orc_mod.canon(fb2), orc_mod.canon(fb))
+    sph, lgt = pkg.synth_scene(6000, 4, seed=2)             # ... and still engages at 6 000
+    fb, _, st = _render(gpu, sph, lgt, 48, 27, -4.0, 1.0, 8)
+    fb2, _, st2 = _render(gpu, sph, lgt, 48, 27, -4.0, 1.0, 8, accel=1)
+    assert st2["accel"] == 1 and np.array_equal(orc_mod.canon(fb2), orc_mod.canon(fb))
 
 
 def test_strips_reassemble_to_the_full_frame(pkg, orc_mod, gpu):
