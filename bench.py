@@ -62,6 +62,7 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-accel", action="store_true", help="skip the optional accelerated-mode leg")
+    ap.add_argument("--phases", action="store_true", help="diagnostic: also time the parts of a step (stderr)")
     ap.add_argument("--verify", action="store_true",
                     help="N>1: rank 0 also renders the whole frame alone and checks the assembled frame is byte-identical")
     return ap.parse_args()
@@ -132,7 +133,7 @@ class ClockSampler:
                 self.power.append(nv.nvmlDeviceGetPowerUsage(self.h) / 1000.0)
             except Exception:
                 pass
-            self._stop.wait(0.05)
+            self._stop.wait(0.2)
 
     def start(self):
         if self.h is not None:
@@ -299,19 +300,33 @@ def run_ours(args):
 
     launches_per_step = 0
 
+    phase_ev = []
+
+    def mark():
+        if args.phases:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record(stream)
+            phase_ev.append(e)
+
     def step_device():
         """One frame, everything on the device.  Returns the number of OUR kernels launched."""
+        mark()
         render()
+        mark()
         k = 1
         if G > 1:
             # global normalisation (algebra.h:68-91): max over shards; non-negative floats order as ints
             xchg.reduce_max(max_bits)
+        mark()
         r.quantise(0.0)
         k += 1
+        mark()
         if G > 1:
             gathered = xchg.gather(rgb_local)
+            mark()
             r.assemble_rgb8(gathered.data_ptr(), frame.data_ptr(), W, H, STRIP_ROWS, G, xchg.pitch)
             k += 1
+        mark()
         return k
 
     def barrier():
@@ -328,7 +343,10 @@ def run_ours(args):
             uuid = str(torch.cuda.get_device_properties(dev).uuid)
         except Exception:
             pass
-        clocks = ClockSampler(local_rank, uuid)
+        # NVML queries take driver locks that can delay kernel launches: one sampler (rank 0's GPU), 5 Hz
+        clocks = ClockSampler(local_rank, uuid if rank == 0 else None)
+        if rank != 0:
+            clocks.h = None
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
         kernel_ms = []
         clocks.start()
@@ -341,6 +359,15 @@ def run_ours(args):
         barrier()
         wall = time.perf_counter() - wall0
         clocks.stop()
+    if args.phases:
+        per = 6 if G > 1 else 4
+        last = phase_ev[-per * args.steps:]
+        names = ["render", "reduce_max", "quantise", "all_gather", "assemble"] if G > 1 else ["render", "-", "quantise"]
+        acc = [0.0] * (per - 1)
+        for i in range(args.steps):
+            for j in range(per - 1):
+                acc[j] += last[i * per + j].elapsed_time(last[i * per + j + 1])
+        print(f"[rank {rank}] phases ms/step: " + ", ".join(f"{n} {a / args.steps:.3f}" for n, a in zip(names, acc)), file=sys.stderr)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
     st = r.stats()
