@@ -178,3 +178,23 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
   if (counters) memcpy(counters, c, sizeof c);
   return 0;
 }
+
+/* The cluster form of a scene (rt_soa.h build_clusters), for tests/test_hostsim.py:
+ * out_rec[nc*4] = the clusters' {Cx, Cy, Cz, w}, out_idx[nc*RT_CLUSTER] = member sphere indices
+ * (0x3FFF = padding).  Returns the number of clusters, or -1. */
+extern "C" int hostsim_clusters(const rt_sphere* spheres, unsigned n, float* out_rec, unsigned short* out_idx,
+                                unsigned capacity) {
+  std::vector<float4_> h;
+  SceneLayout lay;
+  build_scene_soa(spheres, n, nullptr, 0, h, lay);
+  const SceneView sc = scene_view(h.data(), lay);
+  if (sc.nc > capacity) return -1;
+  for (uint32_t c = 0; c < sc.nc; ++c) {
+    out_rec[4 * c + 0] = sc.cfilt[c].x; out_rec[4 * c + 1] = sc.cfilt[c].y;
+    out_rec[4 * c + 2] = sc.cfilt[c].z; out_rec[4 * c + 3] = sc.cfilt[c].w;
+    for (uint32_t m = 0; m < RT_CLUSTER; ++m) out_idx[c * RT_CLUSTER + m] = sc.midx[c * RT_CLUSTER + m];
+  }
+  for (uint32_t c = sc.nc; c < sc.ncPad; ++c)            /* padding clusters must never flag */
+    if (!(sc.cfilt[c].w == INFINITY)) return -2;
+  return (int)sc.nc;
+}

@@ -156,3 +156,43 @@ def test_cluster_filter_rare_paths(pkg, orc_mod, oracle, hostsim):
     a, _ = oracle.render(far, flt, 64, 48, -4.0, 1.0, 8)
     b, cb = hostsim(far, flt, 64, 48, -4.0, 1.0, 8, mode=3)
     assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)) and cb["accel_violations"] == 0
+
+
+def test_cluster_builder_partitions_and_bounds(pkg):
+    """build_clusters (rt_soa.h): every sphere is a member of exactly one cluster, clusters hold <= 8,
+    the bounding record's radius (recovered from w = |C|^2 - R^2 - kappa(|C|^2 + R^2) - ...) reaches past
+    every member, spheres the filter cannot represent sit in always-candidate clusters."""
+    import ctypes
+    import __graft_entry__ as graft
+    lib = ctypes.CDLL(str(graft.build_hostsim()))
+    lib.hostsim_clusters.argtypes = [ctypes.c_void_p, ctypes.c_uint, ctypes.c_void_p, ctypes.c_void_p, ctypes.c_uint]
+    lib.hostsim_clusters.restype = ctypes.c_int
+    kappa = 2.0 ** -17
+    for n, seed, odd in [(1, 0, 0), (8, 1, 0), (9, 2, 0), (100, 3, 0), (1024, 0, 0), (777, 5, 13)]:
+        sph, _ = pkg.synth_scene(n, 1, seed=seed)
+        sph = sph.copy()
+        for k in range(odd):                                   # NaN / infinite geometry
+            sph["pos"][3 + 7 * k] = (np.float32("nan"), 0.0, 0.0) if k % 2 else (np.float32("inf"), 1.0, 2.0)
+        cap = n // 8 + 4
+        rec = np.zeros((cap, 4), np.float32)
+        idx = np.zeros((cap, 8), np.uint16)
+        nc = lib.hostsim_clusters(sph.ctypes.data, n, rec.ctypes.data, idx.ctypes.data, cap)
+        assert 0 < nc <= (n + 7) // 8 + 1
+        members = idx[:nc].reshape(-1)
+        real = members[members != 0x3FFF]
+        assert np.array_equal(np.sort(real), np.arange(n))       # a partition of the spheres
+        finite = np.isfinite(sph["pos"]).all(axis=1) & np.isfinite(sph["radius"])
+        for c in range(nc):
+            m = idx[c][idx[c] != 0x3FFF]
+            assert 1 <= len(m) <= 8
+            if rec[c, 3] == -np.inf:                             # always a candidate
+                assert not finite[m].any()
+                continue
+            assert finite[m].all()
+            C = rec[c, :3].astype(np.float64)
+            cc = float(C @ C)
+            # w <= cc - R^2 - kappa (cc + R^2)  =>  R^2 >= (cc (1 - kappa) - w) / (1 + kappa) - (small terms)
+            R = np.sqrt(max(0.0, (cc * (1 - kappa) - float(rec[c, 3])) / (1 + kappa)))
+            reach = np.linalg.norm(sph["pos"][m].astype(np.float64) - C, axis=1) + np.abs(sph["radius"][m].astype(np.float64))
+            assert (reach <= R * (1 + 1e-6)).all(), (n, c, reach.max(), R)
+            assert R <= 1.25 * reach.max() + 0.3                 # and is not wildly loose
