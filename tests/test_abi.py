@@ -99,3 +99,19 @@ def test_scene_file_round_trip(pkg, tmp_path):
             pkg.load_scene(p)
     with pytest.raises(OSError):
         pkg.load_scene(tmp_path / "missing.txt")
+
+
+def test_stats_struct_matches_the_header(pkg, tmp_path):
+    """The ctypes mirror of rt_cuda_stats has the C struct's size and field offsets."""
+    fields = [n for n, _ in pkg.Stats._fields_]
+    src = tmp_path / "sz.c"
+    lines = ['#include <stdio.h>', '#include <stddef.h>', '#include "rt_cuda.h"', 'int main(void) {',
+             '  printf("%zu\\n", sizeof(rt_cuda_stats));']
+    lines += [f'  printf("%zu\\n", offsetof(rt_cuda_stats, {n}));' for n in fields]
+    lines += ['  return 0; }']
+    src.write_text("\n".join(lines))
+    exe = tmp_path / "sz"
+    subprocess.run(["gcc", "-I", str(ROOT / "include"), "-o", str(exe), str(src)], check=True)
+    out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
+    assert out[0] == ctypes.sizeof(pkg.Stats)
+    assert out[1:] == [getattr(pkg.Stats, n).offset for n in fields]

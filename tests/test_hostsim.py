@@ -196,3 +196,31 @@ def test_cluster_builder_partitions_and_bounds(pkg):
             reach = np.linalg.norm(sph["pos"][m].astype(np.float64) - C, axis=1) + np.abs(sph["radius"][m].astype(np.float64))
             assert (reach <= R * (1 + 1e-6)).all(), (n, c, reach.max(), R)
             assert R <= 1.25 * reach.max() + 0.3                 # and is not wildly loose
+
+
+@pytest.mark.parametrize("seed", [11, 12, 13])
+def test_cluster_filter_audit_under_rescaling(pkg, orc_mod, oracle, hostsim, seed):
+    """The cluster bound's slack terms scale with |o|^2, |c|^2 and r^2: audit translated, shrunk and
+    blown-up copies of random scenes (and mixed radii spanning four decades) — no exactly-accepted sphere
+    may sit in a ruled-out cluster, and the frame stays the oracle's."""
+    rng = np.random.default_rng(seed)
+    sph, lgt = pkg.synth_scene(int(rng.integers(40, 400)), int(rng.integers(1, 5)), seed=seed)
+    variants = []
+    for scale in (np.float32(0.01), np.float32(1.0), np.float32(300.0)):
+        s, l = sph.copy(), lgt.copy()
+        s["pos"] *= scale; s["radius"] *= scale; l["pos"] *= scale
+        variants.append((f"scale {scale}", s, l))
+    s = sph.copy()
+    s["radius"] *= (10.0 ** rng.uniform(-2.5, 1.0, len(s))).astype(np.float32)      # tiny next to huge
+    variants.append(("mixed radii", s, lgt))
+    s = sph.copy()
+    s["pos"][:, 2] -= np.float32(2000.0)                                             # far from the camera
+    variants.append(("far away", s, lgt))
+    s = sph.copy()
+    s["pos"][: len(s) // 2] = s["pos"][0]                                            # half of them concentric
+    variants.append(("concentric", s, lgt))
+    for name, s, l in variants:
+        a, _ = oracle.render(s, l, 48, 36, -4.0, 1.0, 8)
+        b, cb = hostsim(s, l, 48, 36, -4.0, 1.0, 8, mode=3)
+        assert cb["accel_violations"] == 0, (seed, name)
+        assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), (seed, name)
