@@ -39,6 +39,17 @@ namespace rtg {
 #define RT_BLOCK 256
 #endif
 #define RT_LIST_MAX 24
+/* accelerated mode: its loops run over an eighth of the records, so smaller unrolled groups and a single
+ * shadow instance (fewer instructions to fetch per pass) win: 41.9 -> 38.8 ms at 4K / 1 024 spheres */
+#ifndef RT_ACCEL_ONE_SHADOW
+#define RT_ACCEL_ONE_SHADOW 1
+#endif
+#ifndef RT_GROUP_TA
+#define RT_GROUP_TA 8
+#endif
+#ifndef RT_GROUP_CA
+#define RT_GROUP_CA 8
+#endif
 #define RT_LIST1_MAX 40      /* accelerated mode: (sub, cluster) entries per lane between two flushes */
 #define RT_CONST_MAX_SPHERES 1024
 #define RT_NUM_COUNTERS 24
@@ -564,7 +575,7 @@ __device__ __forceinline__ void gather2(const WarpCtx& w, unsigned bits, uint32_
 template <bool USE_CONST>
 __device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                                  int s1, Counters& ctr) {
-  constexpr int G = RT_GROUP_T;
+  constexpr int G = RT_GROUP_TA;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
   DirQ D0, D1;
   D0.ndx = D0.ndy = D0.ndz = D0.od = 0.f; D1 = D0;
@@ -781,7 +792,7 @@ __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx&
 template <bool USE_CONST>
 __device__ __forceinline__ void pass_contain_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                                    int s1, Counters& ctr) {
-  constexpr int G = RT_GROUP_C;
+  constexpr int G = RT_GROUP_CA;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
   bool exact0 = false, exact1 = false;
   if (s0 >= 0) { O0 = make_origin(slots[s0].qo); exact0 = p.noFilter || !origin_filterable(O0); }
@@ -1025,7 +1036,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
       if (sv1 >= 0) prefetch_slot(slots[sv1]);
     }
     if (mode == K_SHADOW) {
-      if (ndMax <= 2) {
+      if (ndMax <= 2 && !(ACCEL && RT_ACCEL_ONE_SHADOW)) {
         if (ACCEL) pass_shadow_accel<USE_CONST, 2>(p, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 2>(p, w, slots, sv0, ctr);
         passS2++;
       } else {
