@@ -50,7 +50,13 @@ namespace rtg {
 #ifndef RT_GROUP_CA
 #define RT_GROUP_CA 8
 #endif
-#define RT_LIST1_MAX 40      /* accelerated mode: (sub, cluster) entries per lane between two flushes */
+#ifndef RT_GROUP_S4A
+#define RT_GROUP_S4A 8
+#endif
+/* accelerated mode: (sub, cluster) entries per lane between two flushes (TraceParams.list1Max, >= 32 because one
+ * group can add 32): 40 is best at 1 024 spheres (more L1 left for the slots), 64 at 4 096 (-10 %, fewer flushes) */
+#define RT_LIST1_SMALL 40
+#define RT_LIST1_LARGE 64
 #define RT_CONST_MAX_SPHERES 1024
 #define RT_NUM_COUNTERS 24
 #define RT_NO_PIXEL 0xFFFFFFFFu
@@ -69,6 +75,7 @@ struct TraceParams {
   uint32_t tilesX, totalWork, chunk;
   int noFilter;             /* debug: exact test for every sphere                   */
   int prefetch;             /* prefetch served slots' state into L1 before the sphere loop */
+  uint32_t list1Max;        /* accelerated mode: capacity of the per-lane (sub, cluster) lists */
 };
 
 __constant__ float4_ c_filt[RT_CONST_MAX_SPHERES];
@@ -618,7 +625,7 @@ __device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& 
         k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
       }
       const unsigned comb = ~k & msk;
-      if (__any_sync(RT_FULL, cnt + __popc(comb) > RT_LIST1_MAX)) { full = true; break; }
+      if (__any_sync(RT_FULL, cnt + __popc(comb) > (int)p.list1Max)) { full = true; break; }
       if (comb) gather1<2, G>(w, comb, base, cnt);
     }
     RT_TICK(2);
@@ -666,7 +673,7 @@ __device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& 
 template <bool USE_CONST, int ND>
 __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
                                                   Counters& ctr) {
-  constexpr int G = (ND == 4) ? RT_GROUP_S4 : RT_GROUP_S2;
+  constexpr int G = (ND == 4) ? RT_GROUP_S4A : RT_GROUP_S2;
   OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
   DirQ D[ND];
   unsigned live = 0u, exact = 0u;
@@ -738,7 +745,7 @@ __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx&
         }
       }
       const unsigned comb = ~sk & msk;
-      if (__any_sync(RT_FULL, cnt + __popc(comb) > RT_LIST1_MAX)) { full = true; break; }
+      if (__any_sync(RT_FULL, cnt + __popc(comb) > (int)p.list1Max)) { full = true; break; }
       if (comb) gather1<ND, G>(w, comb, base, cnt);
     }
     RT_TICK(2);
@@ -823,7 +830,7 @@ __device__ __forceinline__ void pass_contain_accel(const TraceParams& p, WarpCtx
         k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
       }
       const unsigned comb = ~k & msk;
-      if (__any_sync(RT_FULL, cnt + __popc(comb) > RT_LIST1_MAX)) { full = true; break; }
+      if (__any_sync(RT_FULL, cnt + __popc(comb) > (int)p.list1Max)) { full = true; break; }
       if (comb) gather1<2, G>(w, comb, base, cnt);
     }
     RT_TICK(2);
@@ -938,7 +945,7 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
   w.filt = sFilt;
   w.mfilt = sFilt + p.sc.ncPad;
   w.midx = reinterpret_cast<const unsigned short*>(sFilt + (size_t)p.sc.ncPad * (1u + RT_CLUSTER));
-  const uint32_t list1Bytes = ACCEL ? RT_LIST1_MAX * RT_BLOCK * (uint32_t)sizeof(unsigned short) : 0u;
+  const uint32_t list1Bytes = ACCEL ? p.list1Max * RT_BLOCK * (uint32_t)sizeof(unsigned short) : 0u;
   w.list1 = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
   w.list = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes + list1Bytes);
   w.geo = reinterpret_cast<float*>(smem_raw + 16 + filtBytes + list1Bytes + RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short));

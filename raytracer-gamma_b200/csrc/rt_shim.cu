@@ -405,14 +405,16 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if (staging == 1 && (ctx->n == 0 || ctx->nPad > RT_CONST_MAX_SPHERES)) staging = 2;
   /* the accelerated mode needs something to cull and its records in shared memory */
   const size_t perCta = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short) + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float) + 16;
-  const size_t accelBytes = (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) + (size_t)RT_LIST1_MAX * RT_BLOCK * sizeof(unsigned short);
+  const uint32_t list1Max = (ctx->n >= 2048u) ? RT_LIST1_LARGE : RT_LIST1_SMALL;
+  const size_t accelBytes = (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) + (size_t)list1Max * RT_BLOCK * sizeof(unsigned short);
   /* ... and falls back to the plain mode when they do not fit one CTA (> ~8 000 spheres) */
   const bool accel = ctx->accel && !ctx->noFilter && ctx->n >= (ctx->accel == 2 ? 4u * RT_CLUSTER : RT_ACCEL_MIN_SPHERES) &&
                      perCta + accelBytes <= (size_t)ctx->smemOptin;
   if (accel) staging = 2;
   const bool useConst = (staging == 1);
   const size_t sceneBytes = useConst ? 0 : accel ? (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) : (size_t)ctx->nPad * 16;
-  const size_t smem = 16 + sceneBytes + (accel ? (size_t)RT_LIST1_MAX * RT_BLOCK * sizeof(unsigned short) : 0)
+  p.list1Max = list1Max;
+  const size_t smem = 16 + sceneBytes + (accel ? (size_t)list1Max * RT_BLOCK * sizeof(unsigned short) : 0)
                       + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
                       + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
   /* variants: MIN_BLOCKS resident CTAs per SM (register budget), NSLOTS pixels in flight per lane */
