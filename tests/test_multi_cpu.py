@@ -21,7 +21,7 @@ WORKER = textwrap.dedent("""
     par = importlib.import_module(pkg.__name__ + ".parallel")
     dist.init_process_group("gloo")
     rank, world = dist.get_rank(), dist.get_world_size()
-    W, H, alias, S, strip = 70, 45, 2.0, 6, 4
+    W, H, alias, S, strip = 70, int(os.environ.get("RTG_TEST_H", "45")), 2.0, 6, 4
     sph, lgt = pkg.synth_scene(24, 3, seed=5)
     oracle = om.Oracle("port")
     rows = par.shard_rows(H, strip, rank, world)
@@ -56,14 +56,18 @@ WORKER = textwrap.dedent("""
 """) % str(ROOT)
 
 
-def test_two_rank_strip_exchange_gloo(tmp_path, pkg, orc_mod):
+import pytest
+
+
+@pytest.mark.parametrize("world,height", [(2, 45), (3, 50)])      # 50 rows / 4-row strips over 3 ranks: 20, 16 and 14 rows
+def test_strip_exchange_gloo(tmp_path, pkg, orc_mod, world, height):
     graft = sys.modules["__graft_entry__"]
     graft.build_hostsim()
     script = tmp_path / "worker.py"
     script.write_text(WORKER)
-    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1")
-    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
-                          "--master-addr", "127.0.0.1", "--master-port", "29533", str(script)],
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1", OMP_NUM_THREADS="1", RTG_TEST_H=str(height))
+    out = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+                          "--master-addr", "127.0.0.1", "--master-port", str(29533 + world), str(script)],
                          capture_output=True, text=True, env=env, timeout=600)
     assert out.returncode == 0, out.stdout[-2000:] + out.stderr[-4000:]
     assert "MULTI_OK" in out.stdout
