@@ -115,3 +115,17 @@ def test_stats_struct_matches_the_header(pkg, tmp_path):
     out = [int(x) for x in subprocess.run([str(exe)], capture_output=True, text=True, check=True).stdout.split()]
     assert out[0] == ctypes.sizeof(pkg.Stats)
     assert out[1:] == [getattr(pkg.Stats, n).offset for n in fields]
+
+
+def test_reference_side_program_compiles_against_the_reference_headers(pkg):
+    """INTEGRATION.md section 2 as a program (oracle/ref_dropin.cpp): the reference's own structs and
+    setters, pointer casts, the C-ABI.  Here it must build and link; without a GPU it must fail loudly."""
+    import sys
+    graft = sys.modules["__graft_entry__"]
+    if not Path("/root/reference/raytracer_gamma/raytracer.h").exists():
+        pytest.skip("the reference tree is not on this machine")
+    exe = graft.build_dropin()
+    assert exe.exists()
+    if pkg.device_count() == 0:
+        res = subprocess.run([str(exe), "/dev/null"], capture_output=True, text=True, timeout=60)
+        assert res.returncode != 0 and "RT_CUDA_ERR_NO_DEVICE" in res.stdout

@@ -290,6 +290,20 @@ def test_host_program_writes_the_reference_ppm(pkg, tmp_path):
     assert md5[0] == md5[1]
 
 
+def test_reference_structs_through_the_abi(pkg, tmp_path):
+    """oracle/_ref/ref_dropin (built where the reference tree exists, shipped prebuilt): the reference's
+    own `struct Sphere` / `struct Light`, filled by its own setters, cast to the C-ABI's PODs — the PPM
+    is the reference CPU render's, byte for byte."""
+    import subprocess
+    exe = pkg.REPO_ROOT / "oracle" / "_ref" / "ref_dropin"
+    if not exe.exists():
+        pytest.skip("oracle/_ref/ref_dropin was not built (no reference tree at build time)")
+    out = tmp_path / "dropin.ppm"
+    res = subprocess.run([str(exe), str(out)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert hashlib.md5(out.read_bytes()).hexdigest() == FACTS["default_800x600_a3_s6"]["ppm_md5"]
+
+
 def test_full_size_properties_config4(pkg, orc_mod, oracle, gpu):
     """BASELINE config 4 at full size (7680x4320, 1024 spheres, 4 spp, depth 8): 64 rows spread
     over the frame against the oracle (the oracle needs ~0.3 s per row on 16 cores), the
