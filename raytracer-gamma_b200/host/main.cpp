@@ -8,7 +8,7 @@
  *
  *   rt_gamma [--width W] [--height H] [--alias A] [--zoom Z] [--depth S]
  *            [--spheres N] [--lights L] [--seed K] [--device D] [--list]
- *            [--out file.ppm] [--frames F] [--scene file] [--save-scene file] [--accel]
+ *            [--out file.ppm|file.png] [--frames F] [--scene file] [--save-scene file] [--accel]
  */
 #include <chrono>
 #include <cstdio>
@@ -20,6 +20,7 @@
 
 #include "rt_cuda.h"
 #include "rt_scene.h"
+#include "rt_png.h"
 
 /* err_code.h:142-155 keeps print-and-exit as the HOST's policy */
 static void check(int status, const char* what, rt_cuda_ctx* ctx = nullptr) {
@@ -142,7 +143,9 @@ int main(int argc, char** argv) {
          (unsigned long long)(st.rays * st.sph_num), maxColourValue);
   rt_cuda_destroy(ctx);
 
-  if (!save_ppm(rgb.data(), out.c_str(), width, height)) return EXIT_FAILURE;
+  const bool png = out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0;      /* --out x.png: PNG instead of PPM */
+  if (!(png ? rtpng::write_rgb8(out.c_str(), rgb.data(), width, height) : save_ppm(rgb.data(), out.c_str(), width, height)))
+    return EXIT_FAILURE;
   printf("wrote %s\n", out.c_str());
   return 0;
 }

@@ -129,3 +129,40 @@ def test_reference_side_program_compiles_against_the_reference_headers(pkg):
     if pkg.device_count() == 0:
         res = subprocess.run([str(exe), "/dev/null"], capture_output=True, text=True, timeout=60)
         assert res.returncode != 0 and "RT_CUDA_ERR_NO_DEVICE" in res.stdout
+
+
+def test_png_writer_round_trip(tmp_path):
+    """host/rt_png.h (the host program's `--out x.png`): signature, chunk CRCs, zlib stream and pixels
+    survive a decode with Python's zlib."""
+    import struct
+    import zlib
+    W, H = 37, 23
+    rng = np.random.default_rng(3)
+    img = rng.integers(0, 256, (H, W, 3), dtype=np.uint8)
+    big = rng.integers(0, 256, (200, 150, 3), dtype=np.uint8)        # > 65535 raw bytes: several stored blocks
+    src = tmp_path / "png.cpp"
+    src.write_text('#include "rt_png.h"\n#include <stdlib.h>\nint main(int c, char** v) { unsigned w = atoi(v[3]), h = atoi(v[4]);\n'
+                   '  std::vector<unsigned char> b((size_t)w * h * 3); FILE* f = fopen(v[1], "rb");\n'
+                   '  if (!f || fread(b.data(), 1, b.size(), f) != b.size()) return 2; fclose(f);\n'
+                   '  return rtpng::write_rgb8(v[2], b.data(), w, h) ? 0 : 1; }\n')
+    exe = tmp_path / "png"
+    subprocess.run(["g++", "-O1", "-std=c++17", "-I", str(ROOT / "raytracer-gamma_b200" / "host"), "-o", str(exe), str(src)], check=True)
+    for arr in (img, big):
+        raw, out = tmp_path / "in.rgb", tmp_path / "out.png"
+        raw.write_bytes(arr.tobytes())
+        subprocess.run([str(exe), str(raw), str(out), str(arr.shape[1]), str(arr.shape[0])], check=True)
+        data = out.read_bytes()
+        assert data[:8] == b"\x89PNG\r\n\x1a\n"
+        pos, chunks = 8, []
+        while pos < len(data):
+            n, typ = struct.unpack(">I4s", data[pos:pos + 8])
+            body = data[pos + 8:pos + 8 + n]
+            (crc,) = struct.unpack(">I", data[pos + 8 + n:pos + 12 + n])
+            assert crc == zlib.crc32(typ + body) & 0xFFFFFFFF
+            chunks.append((typ, body))
+            pos += 12 + n
+        assert [c[0] for c in chunks] == [b"IHDR", b"IDAT", b"IEND"]
+        w, h, depth, colour, comp, flt, lace = struct.unpack(">IIBBBBB", chunks[0][1])
+        assert (w, h, depth, colour, comp, flt, lace) == (arr.shape[1], arr.shape[0], 8, 2, 0, 0, 0)
+        rows = np.frombuffer(zlib.decompress(chunks[1][1]), np.uint8).reshape(h, w * 3 + 1)
+        assert (rows[:, 0] == 0).all() and np.array_equal(rows[:, 1:].reshape(h, w, 3), arr)

@@ -288,6 +288,20 @@ def test_host_program_writes_the_reference_ppm(pkg, tmp_path):
         assert res.returncode == 0, res.stdout + res.stderr
         md5.append(hashlib.md5(o.read_bytes()).hexdigest())
     assert md5[0] == md5[1]
+    # --out x.png: the same pixels in a PNG (host/rt_png.h)
+    import struct
+    import zlib
+    o = tmp_path / "synth.png"
+    res = subprocess.run([str(pkg.HOST_BIN), "--spheres", "900", "--width", "320", "--height", "180", "--alias", "2",
+                          "--depth", "8", "--out", str(o)], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stdout + res.stderr
+    data = o.read_bytes()
+    assert data[:8] == b"\x89PNG\r\n\x1a\n"
+    n = struct.unpack(">I", data[33:37])[0]                      # IDAT follows the 25-byte IHDR chunk
+    assert data[37:41] == b"IDAT"
+    rows = np.frombuffer(zlib.decompress(data[41:41 + n]), np.uint8).reshape(180, 320 * 3 + 1)
+    ppm = (tmp_path / "synth0.ppm").read_bytes()
+    assert rows[:, 1:].tobytes() == ppm[ppm.index(b"255\n") + 4:]
 
 
 def test_reference_structs_through_the_abi(pkg, tmp_path):
