@@ -8,14 +8,17 @@ frames/s, % of FP32 peak, next to the reference CPU path).
     python bench.py --impl reference --steps 2 --warmup 1      # the reference's CPU path
 
 A "step" is one frame of the workload: trace kernel + device quantise (+ for N > 1 the
-NCCL max all-reduce, RGB8 all-gather and strip assembly).  Default workload = BASELINE
-config 4, the configuration the target is quoted on: synth(1024 spheres, 4 lights),
-7680x4320, alias 2 (4 spp), stack depth 8.  N GPUs render interleaved 16-row strips of the
-SAME frame (strong scaling: total work fixed).
+NCCL max all-reduce, RGB8 all-gather and strip assembly, all inside the C-ABI library
+librt_cuda_multi.so).  Default workload = BASELINE config 4, the configuration the target
+is quoted on: synth(1024 spheres, 4 lights), 7680x4320, alias 2 (4 spp), stack depth 8.
+N GPUs render interleaved 4-row strips of the SAME frame (strong scaling: total work fixed).
 
 One JSON line is printed by rank 0.  `value` is device-timed with the scene resident in
 HBM; `e2e` goes through the C-ABI with host buffers (scene upload H2D + RGB8 readback D2H
-inside the timed region).
+inside the timed region).  At N > 1 the line also carries
+  multi_gpu_frame_identical_to_1gpu   rank 0 renders the frame alone (untimed) and compares bytes
+  native_multi                        the same frame through ONE process driving all N GPUs
+                                      (rt_cuda_multi_init / ncclCommInitAll — what `rt_gamma --gpus N` runs)
 """
 from __future__ import annotations
 
@@ -62,9 +65,8 @@ def parse():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
     ap.add_argument("--no-accel", action="store_true", help="skip the optional accelerated-mode leg")
-    ap.add_argument("--phases", action="store_true", help="diagnostic: also time the parts of a step (stderr)")
-    ap.add_argument("--verify", action="store_true",
-                    help="N>1: rank 0 also renders the whole frame alone and checks the assembled frame is byte-identical")
+    ap.add_argument("--no-native", action="store_true", help="N>1: skip the single-process (ncclCommInitAll) leg")
+    ap.add_argument("--verify", action="store_true", help="accepted for compatibility: the identity check is always on")
     return ap.parse_args()
 
 
@@ -89,7 +91,8 @@ def describe(args, n, l, W, H, alias, S, gpus):
                     f" {W}x{H} alias {alias:g} ({int(np.ceil(alias))**2} spp) stack depth {S}",
         "spheres": 3 if n == 0 else n, "lights": l, "width": W, "height": H, "alias": alias, "max_stack": S,
         "zoom": ZOOM,
-        "parallelism": ("1 GPU" if gpus == 1 else f"{gpus} GPUs x interleaved {STRIP_ROWS}-row strips, NCCL max all-reduce + RGB8 all-gather"),
+        "parallelism": ("1 GPU" if gpus == 1 else f"{gpus} GPUs x interleaved {STRIP_ROWS}-row strips, NCCL max all-reduce + RGB8 all-gather "
+                        "inside librt_cuda_multi.so (one process per GPU)"),
         "l2": "L2 flushed (256 MiB write) before every timed step; the 16 B/px float4 framebuffer also exceeds L2 at this size",
     }
 
@@ -165,43 +168,58 @@ def sample_rows(H: int, count: int):
     return begin, count, step
 
 
-_COUNTER_CACHE: dict = {}
+def host_threads() -> int:
+    """The cores this process may run on.  torchrun exports OMP_NUM_THREADS=1 to its workers, so the
+    OpenMP default is useless there: the CPU legs always pass this count explicitly."""
+    try:
+        return max(1, len(os.sched_getaffinity(0)))
+    except AttributeError:
+        return max(1, os.cpu_count() or 1)
 
 
-def cpu_leg(om, sph, lgt, W, H, alias, S, seconds: float, threads: int = 0):
-    """Time the reference CPU implementation (oracle/_ref when present, else the C port) on
-    a bounded sample of rows of the SAME workload.  -> dict, (rows, framebuffer)"""
-    kind = "reference" if om.reference_available(S) else "port"
-    orc = om.Oracle(kind)
-    port = orc if kind == "port" else om.Oracle("port")
-    cores = om.Oracle("port")._port.rt_oracle_threads() if threads <= 0 else threads
-    # grow the sample until it costs about `seconds` of wall time (row costs vary a lot)
-    count = cores
+def calibrate_rows(orc, sph, lgt, W, H, alias, S, seconds: float, threads: int):
+    """Grow a row sample of the workload's frame until one render of it costs about `seconds`."""
+    count = threads
+    rows = sample_rows(H, count)
     for _ in range(6):
         rows = sample_rows(H, count)
         t0 = time.perf_counter()
-        fb, ctr = orc.render(sph, lgt, W, H, ZOOM, alias, S, rows=rows, threads=threads)
+        orc.render(sph, lgt, W, H, ZOOM, alias, S, rows=rows, threads=threads)
         dt = time.perf_counter() - t0
         if dt >= 0.6 * seconds or rows[1] >= H or count >= H:
             break
         grow = min(8.0, seconds / max(dt, 1e-3))
-        count = int(min(H, max(count + cores, count * grow)))
-        count -= count % cores
+        count = int(min(H, max(count + threads, count * grow)))
+        count -= count % threads
+    return rows
+
+
+def cpu_arm(om, sph, lgt, W, H, alias, S, seconds: float, steps: int, warmup: int):
+    """The reference's CPU implementation (oracle/_ref when present, else the C port) on a bounded, FIXED
+    sample of rows of the workload's frame, all host threads: calibrate the sample once, then time
+    `steps` renders of it.  -> (dict, (rows, framebuffer))"""
+    kind = "reference" if om.reference_available(S) else "port"
+    orc = om.Oracle(kind)
+    threads = host_threads()
+    rows = calibrate_rows(orc, sph, lgt, W, H, alias, S, seconds, threads)
+    times, fb = [], None
+    for i in range(warmup + steps):
+        t0 = time.perf_counter()
+        fb, ctr = orc.render(sph, lgt, W, H, ZOOM, alias, S, rows=rows, threads=threads)
+        if i >= warmup:
+            times.append(time.perf_counter() - t0)
     if kind == "reference":   # the reference has no counters: count the same rows with the port, untimed
-        key = (W, H, alias, S, rows, len(sph), len(lgt))
-        if key not in _COUNTER_CACHE:
-            _COUNTER_CACHE[key] = port.render(sph, lgt, W, H, ZOOM, alias, S, rows=rows, threads=threads)[1]
-        ctr = _COUNTER_CACHE[key]
-    n = len(sph)
+        ctr = om.Oracle("port").render(sph, lgt, W, H, ZOOM, alias, S, rows=rows, threads=threads)[1]
+    dt = float(np.median(times))
     rays = ctr["rays"]
     out = {
-        "value": rays / dt / 1e6, "unit": "Mrays/s", "cores": int(cores), "kind": kind,
-        "sample": f"{rows[1]} of {H} rows (every {rows[2]}th from row {rows[0]}) of the same frame, {rays} rays, {dt:.2f} s wall, "
-                  f"OpenMP dynamic over rows, -O2 -ffp-contract=off",
-        "seconds": dt, "rays": rays,
+        "value": rays / dt / 1e6, "unit": "Mrays/s", "cores": int(threads), "kind": kind,
+        "sample": f"{rows[1]} of {H} rows (every {rows[2]}th from row {rows[0]}) of the same frame, {rays} rays, "
+                  f"median {dt:.2f} s of {len(times)} timed renders, OpenMP dynamic over rows on {threads} threads, -O2 -ffp-contract=off",
+        "seconds": dt, "seconds_all": [round(t, 4) for t in times], "rays": rays,
         "frames_per_s_extrapolated": 1.0 / (dt * H / rows[1]),
         "gflops_17": (FLOP_PER_TEST * ctr["sphere_tests"] + FLOP_PER_CONTAIN * ctr["contain_tests"]) / dt / 1e9,
-        "sphere_tests": ctr["sphere_tests"], "spheres": n,
+        "sphere_tests": ctr["sphere_tests"], "spheres": len(sph),
     }
     return out, (rows, fb)
 
@@ -210,28 +228,23 @@ def run_reference(args):
     rank = int(os.environ.get("RANK", "0"))
     if rank != 0:
         return 0
-    pkg = graft.load_package()
+    pkg = graft.load_package()      # scene builders only (librt_scene.so, host code): no CUDA library is loaded here
     om = graft.load_oracle()
     n, l, W, H, alias, S = workload(args)
     sph, lgt = scene_for(pkg, n, l)
-    times, vals, last = [], [], None
-    for i in range(args.warmup + args.steps):
-        leg, _ = cpu_leg(om, sph, lgt, W, H, alias, S, args.cpu_seconds)
-        if i >= args.warmup:
-            times.append(leg["seconds"])
-            vals.append(leg["value"])
-        last = leg
-    value = float(np.mean(vals))
+    leg, _ = cpu_arm(om, sph, lgt, W, H, alias, S, args.cpu_seconds, args.steps, args.warmup)
+    value = leg["value"]
     line = {
         "impl": "reference", "metric": "Mrays/s", "value": value, "unit": "Mrays/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": float(np.mean(times) * 1e3),
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": leg["seconds"] * 1e3,
         "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": describe(args, n, l, W, H, alias, S, args.gpus),
-        "cpu_baseline": {k: last[k] for k in ("value", "unit", "cores", "kind", "sample")} | {"value": value},
+        "cpu_baseline": {k: leg[k] for k in ("value", "unit", "cores", "kind", "sample")},
         "e2e": {"value": value, "unit": "Mrays/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "frames_per_s": last["frames_per_s_extrapolated"],
-        "note": "each step = the reference CPU render of a bounded row sample of the workload's frame; "
-                "frames_per_s extrapolates the sample to the full frame",
+        "frames_per_s": leg["frames_per_s_extrapolated"], "seconds_per_step": leg["seconds_all"],
+        "note": "each step = the reference CPU render of one fixed, bounded row sample of the workload's frame "
+                "(calibrated once, untimed); value = rays of the sample / median step time; frames_per_s "
+                "extrapolates the sample to the full frame",
     }
     print(json.dumps(line))
     return 0
@@ -260,8 +273,10 @@ def run_ours(args):
         raise SystemExit("bench.py needs a CUDA device: the trace loop has no CPU fallback")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
+    ctl = None
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
+        ctl = dist.new_group(backend="gloo")        # host-side barriers that keep the GPUs idle
 
     pkg = graft.load_package()
     if not pkg.LIB_PATH.exists():
@@ -269,65 +284,32 @@ def run_ours(args):
     n, l, W, H, alias, S = workload(args)
     sph, lgt = scene_for(pkg, n, l)
     G = world
+    frame_bytes = W * H * 3
 
-    r = pkg.Renderer(local_rank)
     stream = torch.cuda.Stream(device=dev)
-    r.set_stream(stream.cuda_stream)
-    import importlib
-    par = importlib.import_module(pkg.__name__ + ".parallel")
-    my_rows = par.shard_rows(H, STRIP_ROWS, rank, G) if G > 1 else np.arange(H)
-    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
-
-    r.upload_scene(sph, lgt)
-
-    def render():
-        if G > 1:
-            r.render_strips(W, H, ZOOM, alias, S, STRIP_ROWS, rank, G)
-        else:
-            r.render(W, H, ZOOM, alias, S)
-
-    # first frame: allocate, learn the device pointers
-    with torch.cuda.stream(stream):
-        render()
-        r.quantise(0.0)
-    r.synchronize()
-    rgb_local = torch.as_tensor(CudaArray(r.device_ptr("rgb8"), len(my_rows) * W * 3), device=dev)
-    max_bits = torch.as_tensor(CudaArray(r.device_ptr("max"), 4, "<i4", 4), device=dev)
     if G > 1:
-        xchg = par.StripExchange(dist, torch, H, W, STRIP_ROWS, rank, G, dev)
-        frame = torch.empty(H * W * 3, dtype=torch.uint8, device=dev)
-    host_frame = torch.empty(H * W * 3, dtype=torch.uint8).pin_memory() if rank == 0 else None
-
-    launches_per_step = 0
-
-    phase_ev = []
-
-    def mark():
-        if args.phases:
-            e = torch.cuda.Event(enable_timing=True)
-            e.record(stream)
-            phase_ev.append(e)
+        # one process per GPU; the exchange (NCCL max all-reduce, RGB8 all-gather) runs inside the C-ABI library
+        box = [pkg.multi_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        r = pkg.MultiRenderer(rank=rank, world=G, uid=box[0], device=local_rank)
+        r.set_stream(stream.cuda_stream)
+    else:
+        r = pkg.Renderer(local_rank)
+        r.set_stream(stream.cuda_stream)
+    flush = torch.empty(256 << 20, dtype=torch.uint8, device=dev)
+    r.upload_scene(sph, lgt)
 
     def step_device():
         """One frame, everything on the device.  Returns the number of OUR kernels launched."""
-        mark()
-        render()
-        mark()
-        k = 1
         if G > 1:
-            # global normalisation (algebra.h:68-91): max over shards; non-negative floats order as ints
-            xchg.reduce_max(max_bits)
-        mark()
+            r.render(W, H, ZOOM, alias, S, STRIP_ROWS)      # trace + combine + quantise + assemble (+ 2 NCCL kernels)
+            return 4 if alias > 1.0 else 3
+        r.render(W, H, ZOOM, alias, S)
         r.quantise(0.0)
-        k += 1
-        mark()
-        if G > 1:
-            gathered = xchg.gather(rgb_local)
-            mark()
-            r.assemble_rgb8(gathered.data_ptr(), frame.data_ptr(), W, H, STRIP_ROWS, G, xchg.pitch)
-            k += 1
-        mark()
-        return k
+        return 3 if alias > 1.0 else 2
+
+    def stats():
+        return r.stats(0) if G > 1 else r.stats()
 
     def barrier():
         if G > 1:
@@ -335,8 +317,9 @@ def run_ours(args):
         torch.cuda.synchronize(dev)
 
     with torch.cuda.stream(stream):
+        launches_per_step = step_device()        # first frame: allocations
         for _ in range(args.warmup):
-            launches_per_step = step_device()
+            step_device()
         barrier()
         uuid = None
         try:
@@ -348,7 +331,6 @@ def run_ours(args):
         if rank != 0:
             clocks.h = None
         ev = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-        kernel_ms = []
         clocks.start()
         wall0 = time.perf_counter()
         for i in range(args.steps):
@@ -359,18 +341,9 @@ def run_ours(args):
         barrier()
         wall = time.perf_counter() - wall0
         clocks.stop()
-    if args.phases:
-        per = 6 if G > 1 else 4
-        last = phase_ev[-per * args.steps:]
-        names = ["render", "reduce_max", "quantise", "all_gather", "assemble"] if G > 1 else ["render", "-", "quantise"]
-        acc = [0.0] * (per - 1)
-        for i in range(args.steps):
-            for j in range(per - 1):
-                acc[j] += last[i * per + j].elapsed_time(last[i * per + j + 1])
-        print(f"[rank {rank}] phases ms/step: " + ", ".join(f"{n} {a / args.steps:.3f}" for n, a in zip(names, acc)), file=sys.stderr)
     step_ms = [a.elapsed_time(b) for a, b in ev]
     total_ms = float(sum(step_ms))
-    st = r.stats()
+    st = stats()
     kernel_ms = st["kernel_ms"]                   # trace kernel of the last timed step (CUDA events in the shim)
 
     # whole-job aggregates: rays over all ranks, time = max over ranks
@@ -395,28 +368,42 @@ def run_ours(args):
     nsph = len(sph)
     flops_frame = FLOP_PER_TEST * live_rays * nsph + FLOP_PER_CONTAIN * contain_tests
 
-    # ---------------- end to end through the C-ABI with host buffers
+    # ---------------- end to end through the C-ABI with host buffers: every step uploads the scene from host
+    # arrays (H2D) and brings the quantised frame back into pinned host memory (D2H, asynchronous: the copy of
+    # frame k overlaps the render of frame k+1; everything has landed before the clock stops)
     e2e = None
     if not args.no_e2e:
-        host_rgb = np.empty((len(my_rows), W, 3), np.uint8)
+        host = [pkg.HostBuffer(frame_bytes), pkg.HostBuffer(frame_bytes)] if rank == 0 else None
         with torch.cuda.stream(stream):
-            def step_e2e():
-                r.upload_scene(sph, lgt)                      # H2D: the scene from host arrays
+            tickets = [None, None]
+
+            def step_e2e(k):
+                r.upload_scene(sph, lgt)                              # H2D: the scene from host arrays
                 if G == 1:
                     r.render(W, H, ZOOM, alias, S)
-                    r.readback_rgb8(0.0, host_rgb)            # device quantise + D2H of 3 B/px
+                    tickets[k & 1] = r.readback_rgb8_async(host[k & 1], 0.0)    # device quantise + D2H of 3 B/px
+                    if k > 0:
+                        r.readback_wait(tickets[(k - 1) & 1])
                 else:
-                    step_device_after_upload()
-            def step_device_after_upload():
-                step_device()
-                if rank == 0:
-                    host_frame.copy_(frame, non_blocking=True)   # D2H of the assembled frame
-                    stream.synchronize()
-            step_e2e()
+                    r.render(W, H, ZOOM, alias, S, STRIP_ROWS)
+                    if rank == 0:
+                        r.readback_wait(0)                            # frame k-1 has landed (one copy in flight)
+                        r.readback_rgb8_async(host[k & 1], 0)         # D2H of the assembled frame
+
+            def finish_e2e(k):
+                if G == 1:
+                    r.readback_wait(tickets[(k - 1) & 1])
+                elif rank == 0:
+                    r.readback_wait(0)
+                r.synchronize()
+
+            step_e2e(0)
+            finish_e2e(1)
             barrier()
             t0 = time.perf_counter()
-            for _ in range(args.steps):
-                step_e2e()
+            for k in range(args.steps):
+                step_e2e(k)
+            finish_e2e(args.steps)
             barrier()
             e2e_s = time.perf_counter() - t0
         t = torch.tensor([e2e_s], dtype=torch.float64, device=dev)
@@ -424,12 +411,13 @@ def run_ours(args):
             dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t[0])
         e2e = {"value": rays * args.steps / e2e_s / 1e6, "unit": "Mrays/s",
-               "h2d_bytes_per_step": int(sph.nbytes + lgt.nbytes) * G, "d2h_bytes_per_step": int(W * H * 3),
+               "h2d_bytes_per_step": int(sph.nbytes + lgt.nbytes) * G, "d2h_bytes_per_step": int(frame_bytes),
                "frames_per_s": args.steps / e2e_s, "ms_per_step": e2e_s / args.steps * 1e3,
-               "path": "rt_cuda_upload_scene (host AoS) -> rt_cuda_render -> rt_cuda_readback_rgb8 (host buffer)"
+               "path": "rt_cuda_upload_scene (host AoS) -> rt_cuda_render -> rt_cuda_readback_rgb8_async (pinned host "
+                       "double buffer; the copy of frame k overlaps the render of frame k+1) -> rt_cuda_readback_wait"
                        if G == 1 else
-                       "rt_cuda_upload_scene -> rt_cuda_render_strips -> NCCL all-reduce(max) -> rt_cuda_quantise -> "
-                       "NCCL all-gather -> rt_cuda_assemble_rgb8 -> D2H to pinned host on rank 0"}
+                       "rt_cuda_multi_upload_scene -> rt_cuda_multi_render (strips, NCCL all-reduce(max), quantise, NCCL "
+                       "all-gather, assemble: inside librt_cuda_multi.so) -> rt_cuda_multi_readback_rgb8_async to pinned host on rank 0"}
 
     # ---------------- optional accelerated mode: same workload, cluster filter on
     accel = None
@@ -438,7 +426,7 @@ def run_ours(args):
         with torch.cuda.stream(stream):
             step_device()
             stream.synchronize()
-            base_rgb = rgb_local.clone()
+            base_rgb = r.readback_rgb8(0)[0].copy() if G > 1 else r.readback_rgb8(0.0).copy()
             r.set_option("accel", 1)
             step_device()
             barrier()
@@ -449,8 +437,9 @@ def run_ours(args):
                 step_device()
                 eva[i][1].record(stream)
             barrier()
-            st_a = r.stats()
-            same = bool(torch.equal(base_rgb, rgb_local))
+            st_a = stats()
+            accel_rgb = r.readback_rgb8(0)[0] if G > 1 else r.readback_rgb8(0.0)
+            same = bool(np.array_equal(base_rgb, accel_rgb))
             r.set_option("accel", 0)
         ta = torch.tensor([sum(a.elapsed_time(b) for a, b in eva), st_a["kernel_ms"], 0.0 if same else 1.0],
                           dtype=torch.float64, device=dev)
@@ -464,6 +453,32 @@ def run_ours(args):
                  "note": "option accel=1: two-level cluster filter, bit-identical frame; not the headline "
                          "(the roofline above is the brute-force kernel's)"}
 
+    # ---------------- N > 1: the assembled frame against the frame rank 0 renders alone (always on), and the
+    # same workload through ONE process driving all N GPUs (the native path of `rt_gamma --gpus N`)
+    identical = native = None
+    if G > 1:
+        with torch.cuda.stream(stream):
+            step_device()
+            stream.synchronize()
+        single = None
+        if rank == 0:
+            multi_frame = r.readback_rgb8(0)[0].copy()
+            with pkg.Renderer(local_rank) as one:
+                one.upload_scene(sph, lgt)
+                one.render(W, H, ZOOM, alias, S)
+                single = one.readback_rgb8(0.0)
+            identical = bool(np.array_equal(multi_frame, single))
+            del multi_frame
+        dist.barrier(group=ctl)
+        if not args.no_native:
+            if rank == 0:
+                try:
+                    native = native_leg(pkg, G, sph, lgt, W, H, alias, S, args, rays, single)
+                except Exception as e:          # reported, never hidden
+                    native = {"error": f"{type(e).__name__}: {e}"}
+            dist.barrier(group=ctl)             # the other ranks wait on the CPU: their GPUs stay idle for rank 0
+        del single
+
     # ---------------- roofline of the dominant kernel (rank 0's trace kernel)
     roofline = cpu = parity = None
     if rank == 0:
@@ -475,7 +490,8 @@ def run_ours(args):
         sm_max = float(peaks.get("sm_max_mhz") or clocks.max_mhz or 1965.0)
         sms = torch.cuda.get_device_properties(dev).multi_processor_count
         peak_nominal = sms * 128 * 2 * sm_max * 1e6 / 1e12
-        ffma = max(r.ffma_peak(8192) for _ in range(3))
+        with pkg.Renderer(local_rank) as probe:
+            ffma = max(probe.ffma_peak(8192) for _ in range(3))
         flops_rank0 = FLOP_PER_TEST * (st["rays"] - st["null_rays"]) * nsph + FLOP_PER_CONTAIN * st["contain_tests"]
         achieved = flops_rank0 / (st["kernel_ms"] * 1e-3) / 1e12
         traffic = None
@@ -504,13 +520,13 @@ def run_ours(args):
             "passes": {"trace": st["passes_trace"], "shadow4": st["passes_shadow4"], "shadow2": st["passes_shadow2"],
                        "contain": st["passes_contain"]},
             "lane_utilisation": (st["active_lane_iters"] / st["lane_iters"]) if st["lane_iters"] else None,
-            "engine": {1: "persistent multi-slot kernel", 2: "wavefront (filter + shade kernels)"}.get(st["engine"]),
+            "engine": "persistent multi-slot kernel",
             "launch": {"grid": st["grid"], "block": st["block"], "smem_bytes": st["smem_bytes"],
-                       "staging": {1: "__constant__", 2: "shared (TMA bulk)"}.get(st["staging"])},
+                       "staging": {1: "constant bank (launch parameter)", 2: "shared (TMA bulk)"}.get(st["staging"])},
         }
         if G == 1 and not args.no_cpu_baseline:
             om = graft.load_oracle()
-            cpu, (rows, ref_fb) = cpu_leg(om, sph, lgt, W, H, alias, S, args.cpu_seconds)
+            cpu, (rows, ref_fb) = cpu_arm(om, sph, lgt, W, H, alias, S, args.cpu_seconds, 1, 0)
             # the same rows on the GPU: a free parity check of the benchmark workload itself
             r.render_strips(W, H, ZOOM, alias, S, 1, rows[0] % rows[2], rows[2])
             got, _ = r.readback()
@@ -520,18 +536,6 @@ def run_ours(args):
                       "within_1lsb_frac": rep["within_1lsb_frac"], "max_lsb_diff": rep["max_lsb_diff"]}
             cpu = {k: cpu[k] for k in ("value", "unit", "cores", "kind", "sample", "frames_per_s_extrapolated",
                                        "gflops_17")}
-
-    identical = None
-    if args.verify and G > 1:
-        with torch.cuda.stream(stream):
-            step_device()
-            stream.synchronize()
-            if rank == 0:
-                multi = frame.cpu().numpy().reshape(H, W, 3)
-                r.render(W, H, ZOOM, alias, S)
-                single = r.readback_rgb8(0.0)
-                identical = bool(np.array_equal(multi, single))
-        barrier()
 
     if rank == 0:
         line = {
@@ -549,14 +553,58 @@ def run_ours(args):
             "roofline": roofline, "cpu_baseline": cpu, "parity_sample": parity,
             "accelerated_mode": accel,
         }
-        if identical is not None:
+        if G > 1:
             line["multi_gpu_frame_identical_to_1gpu"] = identical
+            line["native_multi"] = native
         print(json.dumps(line))
     r.close()
     if G > 1:
         dist.barrier()
         dist.destroy_process_group()
     return 0
+
+
+def native_leg(pkg, G, sph, lgt, W, H, alias, S, args, rays, single_frame):
+    """The workload through ONE process driving all G GPUs of the box: rt_cuda_multi_init (ncclCommInitAll,
+    one stream per device), no Python in the data path.  Device-timed per step with CUDA events on every
+    device's stream (the library's), max over devices; L2 flushed on every device between steps."""
+    with pkg.MultiRenderer(gpus=G) as m:
+        m.upload_scene(sph, lgt)
+        for _ in range(max(1, args.warmup)):
+            m.render(W, H, ZOOM, alias, S, STRIP_ROWS)
+        m.synchronize()
+        ms = []
+        for _ in range(args.steps):
+            m.flush_l2()
+            m.synchronize()
+            m.render(W, H, ZOOM, alias, S, STRIP_ROWS)
+            m.synchronize()
+            ms.append(max(m.step_ms(g) for g in range(G)))
+        frame, _ = m.readback_rgb8(0)
+        kern = [m.stats(g)["kernel_ms"] for g in range(G)]
+        # end to end from host buffers, frames pipelined (upload H2D every step, async D2H into pinned memory)
+        host = [pkg.HostBuffer(W * H * 3), pkg.HostBuffer(W * H * 3)]
+        t0 = time.perf_counter()
+        for k in range(args.steps):
+            m.upload_scene(sph, lgt)
+            m.render(W, H, ZOOM, alias, S, STRIP_ROWS)
+            m.readback_wait(0)
+            m.readback_rgb8_async(host[k & 1], 0)
+        m.readback_wait(0)
+        m.synchronize()
+        e2e_s = time.perf_counter() - t0
+        same_e2e = bool(np.array_equal(host[(args.steps - 1) & 1].array.reshape(H, W, 3), frame))
+        for h in host:
+            h.free()
+    total = float(sum(ms))
+    return {"value": rays * args.steps / (total * 1e-3) / 1e6, "unit": "Mrays/s", "ms_per_step": total / args.steps,
+            "frames_per_s": args.steps * 1e3 / total, "steps": args.steps,
+            "trace_kernel_ms_per_device": [round(k, 3) for k in kern],
+            "frame_identical_to_1gpu": bool(np.array_equal(frame, single_frame)),
+            "e2e": {"value": rays * args.steps / e2e_s / 1e6, "unit": "Mrays/s", "frames_per_s": args.steps / e2e_s,
+                    "ms_per_step": e2e_s / args.steps * 1e3, "frame_identical": same_e2e},
+            "path": "one process, rt_cuda_multi_init(G) = ncclCommInitAll + one stream per device; timed with CUDA events "
+                    "on each device's stream, max over devices"}
 
 
 def main():

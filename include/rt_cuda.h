@@ -8,10 +8,18 @@
  *                           (+ device_info.cpp:30-125 via rt_cuda_device_info)
  *   rt_cuda_upload_scene    main.cpp:277-294  clCreateBuffer x2 + clEnqueueWriteBuffer x2
  *   rt_cuda_render          main.cpp:339-362  clSetKernelArg 0-10 + clEnqueueNDRangeKernel + clFinish
- *                           of `__kernel raytrace` (raytrace_kernel.cl:870-973); same result as the
- *                           CPU loop main.cpp:404-453 around rayTrace() (raytracer.h:410)
+ *                           of `__kernel raytrace` (raytrace_kernel.cl:870-973).  PARITY TARGET: the CPU
+ *                           copy of the algorithm — the loop main.cpp:404-453 around rayTrace()
+ *                           (raytracer.h:410) — reproduced bit for bit.  The OpenCL copy differs from it
+ *                           in two places: polarisedReflection is all-float there (raytrace_kernel.cl:
+ *                           399-432; double on the CPU, raytracer.h:380-393) and its RTSTACK_MAXSIZE is 5
+ *                           (raytrace_kernel.cl:58; 6 on the CPU, raytraceStack.h:10).  Pass maxStack = 5
+ *                           for kernel-equivalent recursion depth; the Fresnel difference stays within
+ *                           the 1-LSB 8-bit tolerance.
  *   rt_cuda_readback        main.cpp:456-471  clEnqueueReadBuffer + maxColourValuePixelBuffer (algebra.h:68)
  *   rt_cuda_readback_rgb8   main.cpp:71-76    the quantiser of savePPM, on the device
+ *   rt_cuda_readback_rgb8_async / rt_cuda_readback_wait   the same, overlapped with the next frame's render
+ *                           (the reference blocks in clEnqueueReadBuffer(CL_TRUE), main.cpp:460)
  *   rt_cuda_destroy         main.cpp:483-489  clRelease*
  *   rt_cuda_strerror        err_code.h:31-140 err_code()
  *
@@ -44,7 +52,8 @@ typedef enum rt_cuda_status {
   RT_CUDA_ERR_NO_SCENE = -4,
   RT_CUDA_ERR_NO_FRAME = -5,
   RT_CUDA_ERR_TOO_LARGE = -6,
-  RT_CUDA_ERR_OUT_OF_MEMORY = -7
+  RT_CUDA_ERR_OUT_OF_MEMORY = -7,
+  RT_CUDA_ERR_NCCL = -8           /* multi-GPU library only (rt_cuda_multi.h) */
 } rt_cuda_status;
 
 /* Limits of this implementation */
@@ -72,8 +81,8 @@ typedef struct rt_cuda_stats {
   float    kernel_ms;       /* trace kernel only, CUDA events on the context's stream               */
   float    max_colour;      /* NaN-skipping max of this context's rows, 0 if all black              */
   uint32_t kernel_launches; /* kernels this library launched since the last render began            */
-  uint32_t grid, block, smem_bytes, staging;   /* launch shape; staging 1 = __constant__, 2 = shared via TMA bulk */
-  uint32_t engine;          /* 1 = persistent multi-slot kernel, 2 = wavefront (filter + shade kernels) */
+  uint32_t grid, block, smem_bytes, staging;   /* launch shape; staging 1 = constant bank (launch parameter), 2 = shared via TMA bulk */
+  uint32_t engine;          /* 1 = persistent multi-slot kernel (the only engine) */
   uint32_t accel;           /* 1 = this frame used the two-level cluster filter (option "accel")    */
   uint32_t clusters;        /* ... over this many sphere clusters                                   */
   uint32_t reserved_;
@@ -112,6 +121,20 @@ int rt_cuda_readback_rgb8(rt_cuda_ctx* ctx, unsigned char* dst, float maxColour)
 
 /* Device-side quantise only (result stays in rt_cuda_device_rgb8). */
 int rt_cuda_quantise(rt_cuda_ctx* ctx, float maxColour);
+/* ... into caller-provided device memory (4-byte aligned, >= localRows*W*3 bytes), e.g. this
+ * rank's block of an all-gather buffer. */
+int rt_cuda_quantise_to(rt_cuda_ctx* ctx, void* devDst, size_t dstBytes, float maxColour);
+
+/* Asynchronous readback.  Quantises the frame just rendered on the
+ * context's stream and copies it to dst on a second stream; returns at once with a ticket
+ * (0 or 1).  dst is complete after rt_cuda_readback_wait(ctx, ticket).  The next
+ * rt_cuda_render may be issued immediately: it overlaps the copy.  Two readbacks can be
+ * in flight; a third call first waits for the oldest.  dst from rt_cuda_host_alloc
+ * (pinned) is written by DMA directly; any other memory is staged and filled by the wait. */
+int rt_cuda_readback_rgb8_async(rt_cuda_ctx* ctx, unsigned char* dst, float maxColour, int* ticket);
+int rt_cuda_readback_wait(rt_cuda_ctx* ctx, int ticket);
+void* rt_cuda_host_alloc(size_t bytes);          /* page-locked host memory, NULL on failure */
+void  rt_cuda_host_free(void* p);
 
 /* Device pointers for multi-GPU plumbing (NCCL gather / max all-reduce). */
 void* rt_cuda_device_packed(rt_cuda_ctx* ctx);   /* float[localRows*W*3], valid after rt_cuda_pack   */
@@ -121,14 +144,16 @@ int   rt_cuda_pack(rt_cuda_ctx* ctx);            /* float4 framebuffer -> packed
 
 /* Use an existing cudaStream_t (e.g. the framework's current stream). */
 int rt_cuda_set_stream(rt_cuda_ctx* ctx, void* cudaStream);
+void* rt_cuda_get_stream(rt_cuda_ctx* ctx);      /* the cudaStream_t the context launches on */
+int rt_cuda_get_device(rt_cuda_ctx* ctx);
 int rt_cuda_synchronize(rt_cuda_ctx* ctx);
+/* Benchmark aid: overwrite a 256 MiB scratch buffer on the context's stream (evicts the 126 MB L2). */
+int rt_cuda_flush_l2(rt_cuda_ctx* ctx);
 
-/* Tuning / debug switches: "staging" 0 auto | 1 __constant__ | 2 shared (TMA bulk);
+/* Tuning / debug switches: "staging" 0 auto (= 2) | 1 constant bank: the filter records travel as a
+ *   __grid_constant__ launch parameter, <= 1024 spheres | 2 shared memory filled by TMA bulk copies;
  * "no_filter" 1 = exact test against every sphere; "blocks_per_sm" 0 auto;
- * "min_blocks" 0 auto | 2 | 3 = register-budget variant of the trace kernel;
- * "slots" 0 auto | 2 | 3 | 4 = pixels in flight per lane;
- * "engine" 0 auto (= 1) | 1 persistent kernel | 2 wavefront (slower; kept as a measured alternative);
- * "pool" = wavefront samples in flight;
+ * (development builds, -DRT_DEV_VARIANTS: "min_blocks" 2 | 3, "slots" 2 | 3 | 4, "prefetch");
  * "accel" 0 off | 1 = two-level cluster filter where it pays (>= 768 spheres) | 2 = from 32 spheres.
  *   Same frame bit for bit; fewer filter tests.  Off by default: the reference's
  *   algorithm is brute force and the default kernel is measured against that roofline. */

@@ -21,6 +21,8 @@ import numpy as np
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
 LIB_PATH = Path(os.environ.get("RTG_LIB", PKG_DIR / "librt_cuda.so"))   # RTG_LIB: development override
+SCENE_LIB_PATH = PKG_DIR / "librt_scene.so"          # host-only: scene builders (no CUDA in it)
+MULTI_LIB_PATH = PKG_DIR / "librt_cuda_multi.so"     # multi-GPU sequencing over librt_cuda.so + NCCL
 HOST_BIN = PKG_DIR / "rt_gamma"
 
 # Layout of the reference PODs (sphere.h:9-14, raytracer.h:20-25, vec.h:27-29)
@@ -36,27 +38,40 @@ NVCC_FLAGS = [
 ]
 
 
+def _stale(out: Path, deps) -> bool:
+    return not out.exists() or out.stat().st_mtime < max(p.stat().st_mtime for p in deps)
+
+
 def build(force: bool = False, verbose: bool = False) -> Path:
-    """Compile librt_cuda.so (and the C++ host program) in-tree for sm_100a."""
-    srcs = [PKG_DIR / "csrc" / "rt_shim.cu", PKG_DIR / "host" / "rt_scene.c"]
-    deps = srcs + list((PKG_DIR / "csrc").glob("*.cuh")) + list((PKG_DIR / "csrc").glob("*.h")) + \
-        list((REPO_ROOT / "include").glob("*.h"))
-    newest = max(p.stat().st_mtime for p in deps)
-    if force or not LIB_PATH.exists() or LIB_PATH.stat().st_mtime < newest:
-        cmd = ["nvcc", *NVCC_FLAGS, "-shared", f"-I{REPO_ROOT / 'include'}", f"-I{PKG_DIR / 'csrc'}",
-               "-o", str(LIB_PATH), *map(str, srcs)]
+    """Compile in-tree: librt_scene.so (gcc, host only), librt_cuda.so (nvcc, sm_100a),
+    librt_cuda_multi.so (NCCL sequencing) and the C++ host program rt_gamma."""
+    def run(cmd):
         if verbose:
-            print(" ".join(cmd))
-        subprocess.run(cmd, check=True)
+            print(" ".join(map(str, cmd)))
+        subprocess.run(list(map(str, cmd)), check=True)
+
+    inc = list((REPO_ROOT / "include").glob("*.h"))
+    scene_src = PKG_DIR / "host" / "rt_scene.c"
+    if force or _stale(SCENE_LIB_PATH, [scene_src] + inc):
+        run(["gcc", "-O2", "-std=c11", "-ffp-contract=off", "-fPIC", "-shared", f"-I{REPO_ROOT / 'include'}",
+             "-o", SCENE_LIB_PATH, scene_src, "-lm"])
+    lib = PKG_DIR / "librt_cuda.so"
+    deps = [PKG_DIR / "csrc" / "rt_shim.cu"] + list((PKG_DIR / "csrc").glob("*.cuh")) + \
+        list((PKG_DIR / "csrc").glob("*.h")) + inc
+    if force or _stale(lib, deps):
+        run(["nvcc", *NVCC_FLAGS, "-shared", f"-I{REPO_ROOT / 'include'}", f"-I{PKG_DIR / 'csrc'}",
+             "-o", lib, PKG_DIR / "csrc" / "rt_shim.cu"])
+    multi_src = PKG_DIR / "csrc" / "rt_multi.cpp"
+    if force or _stale(MULTI_LIB_PATH, [multi_src, lib] + inc):
+        run(["nvcc", "-O2", "-std=c++17", "-Xcompiler", "-fPIC", "-shared", f"-I{REPO_ROOT / 'include'}",
+             "-o", MULTI_LIB_PATH, multi_src, f"-L{PKG_DIR}", "-lrt_cuda", "-lnccl",
+             "-Xlinker", "-rpath", "-Xlinker", "$ORIGIN"])
     host_src = PKG_DIR / "host" / "main.cpp"
-    if host_src.exists() and (force or not HOST_BIN.exists()
-                              or HOST_BIN.stat().st_mtime < max(newest, host_src.stat().st_mtime)):
-        cmd = ["g++", "-O2", "-std=c++17", "-ffp-contract=off", f"-I{REPO_ROOT / 'include'}",
-               "-o", str(HOST_BIN), str(host_src), f"-L{PKG_DIR}", "-lrt_cuda",
-               f"-Wl,-rpath,{PKG_DIR}", "-Wl,-rpath,$ORIGIN"]
-        if verbose:
-            print(" ".join(cmd))
-        subprocess.run(cmd, check=True)
+    host_deps = [host_src, PKG_DIR / "host" / "rt_png.h", lib, SCENE_LIB_PATH, MULTI_LIB_PATH] + inc
+    if host_src.exists() and (force or _stale(HOST_BIN, host_deps)):
+        run(["g++", "-O2", "-std=c++17", "-ffp-contract=off", f"-I{REPO_ROOT / 'include'}",
+             "-o", HOST_BIN, host_src, f"-L{PKG_DIR}", "-lrt_cuda_multi", "-lrt_cuda", "-lrt_scene",
+             "-Wl,-rpath,$ORIGIN", f"-Wl,-rpath-link,{PKG_DIR}"])
     return LIB_PATH
 
 
@@ -107,6 +122,14 @@ C_ABI = [
     ("rt_cuda_readback", ctypes.c_int, [_P, _P, ctypes.POINTER(ctypes.c_float)]),
     ("rt_cuda_readback_rgb8", ctypes.c_int, [_P, _P, ctypes.c_float]),
     ("rt_cuda_quantise", ctypes.c_int, [_P, ctypes.c_float]),
+    ("rt_cuda_quantise_to", ctypes.c_int, [_P, _P, ctypes.c_size_t, ctypes.c_float]),
+    ("rt_cuda_readback_rgb8_async", ctypes.c_int, [_P, _P, ctypes.c_float, ctypes.POINTER(ctypes.c_int)]),
+    ("rt_cuda_readback_wait", ctypes.c_int, [_P, ctypes.c_int]),
+    ("rt_cuda_host_alloc", _P, [ctypes.c_size_t]),
+    ("rt_cuda_host_free", None, [_P]),
+    ("rt_cuda_get_stream", _P, [_P]),
+    ("rt_cuda_get_device", ctypes.c_int, [_P]),
+    ("rt_cuda_flush_l2", ctypes.c_int, [_P]),
     ("rt_cuda_device_packed", _P, [_P]),
     ("rt_cuda_device_rgb8", _P, [_P]),
     ("rt_cuda_device_max", _P, [_P]),
@@ -123,6 +146,10 @@ C_ABI = [
     ("rt_cuda_last_error", ctypes.c_char_p, [_P]),
     ("rt_cuda_device_count", ctypes.c_int, []),
     ("rt_cuda_device_info", ctypes.c_int, [ctypes.c_int, ctypes.c_char_p, ctypes.c_size_t]),
+]
+
+# include/rt_scene.h (librt_scene.so, host only)
+SCENE_ABI = [
     ("rt_make_material", None,
      [_P, _P, _P, ctypes.c_float, ctypes.c_float, ctypes.c_float]),
     ("rt_scene_default", None, [_P, _P]),
@@ -133,23 +160,72 @@ C_ABI = [
     ("rt_scene_free", None, [_P]),
 ]
 
+# include/rt_cuda_multi.h (librt_cuda_multi.so)
+MULTI_ABI = [
+    ("rt_cuda_multi_shard_rows", ctypes.c_uint, [ctypes.c_uint] * 4),
+    ("rt_cuda_multi_shard_pitch", ctypes.c_size_t, [ctypes.c_uint] * 4),
+    ("rt_cuda_multi_locate_row", None, [ctypes.c_uint] * 3 + [ctypes.POINTER(ctypes.c_uint)] * 2),
+    ("rt_cuda_multi_init", ctypes.c_int, [ctypes.c_int, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_P)]),
+    ("rt_cuda_multi_unique_id", ctypes.c_int, [_P, ctypes.c_size_t]),
+    ("rt_cuda_multi_init_rank", ctypes.c_int, [ctypes.c_int, _P, ctypes.c_size_t, ctypes.c_int, ctypes.c_int,
+                                               ctypes.POINTER(_P)]),
+    ("rt_cuda_multi_world_size", ctypes.c_int, [_P]),
+    ("rt_cuda_multi_local_count", ctypes.c_int, [_P]),
+    ("rt_cuda_multi_context", _P, [_P, ctypes.c_int]),
+    ("rt_cuda_multi_upload_scene", ctypes.c_int, [_P, _P, ctypes.c_uint, _P, ctypes.c_uint]),
+    ("rt_cuda_multi_set_option", ctypes.c_int, [_P, ctypes.c_char_p, ctypes.c_long]),
+    ("rt_cuda_multi_render", ctypes.c_int,
+     [_P, ctypes.c_uint, ctypes.c_uint, ctypes.c_float, ctypes.c_float, ctypes.c_int, ctypes.c_uint]),
+    ("rt_cuda_multi_synchronize", ctypes.c_int, [_P]),
+    ("rt_cuda_multi_device_frame", _P, [_P, ctypes.c_int]),
+    ("rt_cuda_multi_readback_rgb8", ctypes.c_int, [_P, ctypes.c_int, _P, ctypes.POINTER(ctypes.c_float)]),
+    ("rt_cuda_multi_readback_rgb8_async", ctypes.c_int, [_P, ctypes.c_int, _P]),
+    ("rt_cuda_multi_readback_wait", ctypes.c_int, [_P, ctypes.c_int]),
+    ("rt_cuda_multi_step_ms", ctypes.c_int, [_P, ctypes.c_int, ctypes.POINTER(ctypes.c_float)]),
+    ("rt_cuda_multi_flush_l2", ctypes.c_int, [_P]),
+    ("rt_cuda_multi_last_error", ctypes.c_char_p, [_P]),
+    ("rt_cuda_multi_destroy", None, [_P]),
+]
+
 _LIB = None
+_SCENE_LIB = None
+_MULTI_LIB = None
+
+
+def _bind(path: Path, table) -> ctypes.CDLL:
+    if not path.exists():
+        raise FileNotFoundError(
+            f"{path} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
+            "There is no CPU fallback for the trace loop.")
+    lib = ctypes.CDLL(str(path), mode=ctypes.RTLD_GLOBAL)
+    for name, res, args in table:
+        fn = getattr(lib, name)
+        fn.restype = res
+        fn.argtypes = args
+    return lib
 
 
 def _lib() -> ctypes.CDLL:
     global _LIB
     if _LIB is None:
-        if not LIB_PATH.exists():
-            raise FileNotFoundError(
-                f"{LIB_PATH} is missing: run __graft_entry__.build() (nvcc, sm_100a). "
-                "There is no CPU fallback for the trace loop.")
-        lib = ctypes.CDLL(str(LIB_PATH))
-        for name, res, args in C_ABI:
-            fn = getattr(lib, name)
-            fn.restype = res
-            fn.argtypes = args
-        _LIB = lib
+        _LIB = _bind(LIB_PATH, C_ABI)
     return _LIB
+
+
+def _scene_lib() -> ctypes.CDLL:
+    global _SCENE_LIB
+    if _SCENE_LIB is None:
+        _SCENE_LIB = _bind(SCENE_LIB_PATH, SCENE_ABI)
+    return _SCENE_LIB
+
+
+def _multi_lib() -> ctypes.CDLL:
+    """librt_cuda_multi.so: needs librt_cuda.so (loaded first, so an RTG_LIB override is honoured) and NCCL."""
+    global _MULTI_LIB
+    if _MULTI_LIB is None:
+        _lib()
+        _MULTI_LIB = _bind(MULTI_LIB_PATH, MULTI_ABI)
+    return _MULTI_LIB
 
 
 def load() -> ctypes.CDLL:
@@ -173,7 +249,7 @@ def default_scene():
     """The scene literal of main.cpp:113-168 as (spheres, lights) structured arrays."""
     sph = np.zeros(3, SPHERE_DTYPE)
     lgt = np.zeros(2, LIGHT_DTYPE)
-    _lib().rt_scene_default(sph.ctypes.data, lgt.ctypes.data)
+    _scene_lib().rt_scene_default(sph.ctypes.data, lgt.ctypes.data)
     return sph, lgt
 
 
@@ -181,7 +257,7 @@ def synth_scene(n: int, lights: int = 4, seed: int = 0):
     """synth(N, L, seed) of SURVEY.md §8(d)."""
     sph = np.zeros(n, SPHERE_DTYPE)
     lgt = np.zeros(lights, LIGHT_DTYPE)
-    rc = _lib().rt_scene_synth(n, lights, seed, sph.ctypes.data, lgt.ctypes.data)
+    rc = _scene_lib().rt_scene_synth(n, lights, seed, sph.ctypes.data, lgt.ctypes.data)
     if rc:
         raise ValueError("rt_scene_synth: bad arguments")
     return sph, lgt
@@ -190,7 +266,7 @@ def synth_scene(n: int, lights: int = 4, seed: int = 0):
 def save_scene(path, spheres: np.ndarray, lights: np.ndarray) -> None:
     spheres = np.ascontiguousarray(spheres)
     lights = np.ascontiguousarray(lights)
-    rc = _lib().rt_scene_save(str(path).encode(), spheres.ctypes.data if len(spheres) else None, len(spheres),
+    rc = _scene_lib().rt_scene_save(str(path).encode(), spheres.ctypes.data if len(spheres) else None, len(spheres),
                               lights.ctypes.data if len(lights) else None, len(lights))
     if rc:
         raise OSError(f"rt_scene_save({path}) failed")
@@ -199,7 +275,7 @@ def save_scene(path, spheres: np.ndarray, lights: np.ndarray) -> None:
 def load_scene(path):
     ps, pl = _P(), _P()
     ns, nl = ctypes.c_uint(0), ctypes.c_uint(0)
-    rc = _lib().rt_scene_load(str(path).encode(), ctypes.byref(ps), ctypes.byref(ns), ctypes.byref(pl), ctypes.byref(nl))
+    rc = _scene_lib().rt_scene_load(str(path).encode(), ctypes.byref(ps), ctypes.byref(ns), ctypes.byref(pl), ctypes.byref(nl))
     if rc:
         raise OSError(f"rt_scene_load({path}) failed")
     try:
@@ -210,8 +286,8 @@ def load_scene(path):
         if nl.value:
             ctypes.memmove(lgt.ctypes.data, pl, lgt.nbytes)
     finally:
-        _lib().rt_scene_free(ps)
-        _lib().rt_scene_free(pl)
+        _scene_lib().rt_scene_free(ps)
+        _scene_lib().rt_scene_free(pl)
     return sph, lgt
 
 
@@ -219,7 +295,7 @@ def make_material(matte, gloss, opacity, gloss_factor, refractive_index) -> np.n
     out = np.zeros(8, np.float32)
     m = np.asarray(matte, np.float32)
     g = np.asarray(gloss, np.float32)
-    _lib().rt_make_material(out.ctypes.data, m.ctypes.data, g.ctypes.data, opacity, gloss_factor,
+    _scene_lib().rt_make_material(out.ctypes.data, m.ctypes.data, g.ctypes.data, opacity, gloss_factor,
                             refractive_index)
     return out
 
@@ -306,6 +382,26 @@ class Renderer:
     def quantise(self, max_colour: float = 0.0):
         self._check(self._lib.rt_cuda_quantise(self._ctx, max_colour), "rt_cuda_quantise")
 
+    def quantise_to(self, dev_ptr: int, nbytes: int, max_colour: float = 0.0):
+        self._check(self._lib.rt_cuda_quantise_to(self._ctx, _P(dev_ptr), nbytes, max_colour), "rt_cuda_quantise_to")
+
+    def readback_rgb8_async(self, out: "HostBuffer | np.ndarray", max_colour: float = 0.0) -> int:
+        """Enqueue quantise + D2H into `out` (a HostBuffer = pinned, or any uint8 array) and return a ticket."""
+        arr = out.array if isinstance(out, HostBuffer) else out
+        t = ctypes.c_int(-1)
+        self._check(self._lib.rt_cuda_readback_rgb8_async(self._ctx, arr.ctypes.data, max_colour, ctypes.byref(t)),
+                    "rt_cuda_readback_rgb8_async")
+        return t.value
+
+    def readback_wait(self, ticket: int):
+        self._check(self._lib.rt_cuda_readback_wait(self._ctx, ticket), "rt_cuda_readback_wait")
+
+    def flush_l2(self):
+        self._check(self._lib.rt_cuda_flush_l2(self._ctx), "rt_cuda_flush_l2")
+
+    def stream(self) -> int:
+        return int(self._lib.rt_cuda_get_stream(self._ctx) or 0)
+
     def pack(self):
         self._check(self._lib.rt_cuda_pack(self._ctx), "rt_cuda_pack")
 
@@ -330,6 +426,154 @@ class Renderer:
         fn = {"packed": self._lib.rt_cuda_device_packed, "rgb8": self._lib.rt_cuda_device_rgb8,
               "max": self._lib.rt_cuda_device_max}[which]
         return int(fn(self._ctx) or 0)
+
+
+class HostBuffer:
+    """Page-locked host memory from rt_cuda_host_alloc, viewed as a uint8 numpy array."""
+
+    def __init__(self, nbytes: int):
+        self._lib = _lib()
+        self.ptr = self._lib.rt_cuda_host_alloc(nbytes)
+        if not self.ptr:
+            raise MemoryError(f"rt_cuda_host_alloc({nbytes}) failed")
+        self.array = np.ctypeslib.as_array((ctypes.c_uint8 * nbytes).from_address(self.ptr))
+
+    def free(self):
+        if self.ptr:
+            self.array = None
+            self._lib.rt_cuda_host_free(self.ptr)
+            self.ptr = None
+
+    def __del__(self):
+        try:
+            self.free()
+        except Exception:
+            pass
+
+
+def multi_layout(width: int, height: int, strip_rows: int, world: int) -> dict:
+    """Rows per rank and the gather pitch as librt_cuda_multi.so computes them (host arithmetic only)."""
+    lib = _multi_lib()
+    return {"rows": [lib.rt_cuda_multi_shard_rows(height, strip_rows, g, world) for g in range(world)],
+            "pitch": lib.rt_cuda_multi_shard_pitch(width, height, strip_rows, world)}
+
+
+def multi_locate_row(row: int, strip_rows: int, world: int):
+    r, lr = ctypes.c_uint(0), ctypes.c_uint(0)
+    _multi_lib().rt_cuda_multi_locate_row(row, strip_rows, world, ctypes.byref(r), ctypes.byref(lr))
+    return r.value, lr.value
+
+
+def multi_unique_id() -> bytes:
+    buf = ctypes.create_string_buffer(128)
+    rc = _multi_lib().rt_cuda_multi_unique_id(buf, 128)
+    if rc:
+        raise RtCudaError(rc, "rt_cuda_multi_unique_id")
+    return buf.raw
+
+
+class MultiRenderer:
+    """One frame sharded by row strips over several GPUs (include/rt_cuda_multi.h).
+
+    MultiRenderer(gpus=N)                      one process drives N devices (ncclCommInitAll)
+    MultiRenderer(rank=r, world=G, uid=bytes, device=d)   one process per GPU (torchrun)"""
+
+    def __init__(self, gpus: int | None = None, devices=None, *, rank: int | None = None, world: int | None = None,
+                 uid: bytes | None = None, device: int = 0):
+        self._lib = _multi_lib()
+        self._m = _P()
+        if rank is None:
+            arr = (ctypes.c_int * gpus)(*devices) if devices is not None else None
+            rc = self._lib.rt_cuda_multi_init(gpus, arr, ctypes.byref(self._m))
+            where = "rt_cuda_multi_init"
+        else:
+            rc = self._lib.rt_cuda_multi_init_rank(device, uid, len(uid), rank, world, ctypes.byref(self._m))
+            where = "rt_cuda_multi_init_rank"
+        if rc:
+            raise RtCudaError(rc, where)
+        self.world = self._lib.rt_cuda_multi_world_size(self._m)
+        self.local = self._lib.rt_cuda_multi_local_count(self._m)
+        self.width = self.height = 0
+
+    def _check(self, rc: int, where: str):
+        if rc:
+            raise RtCudaError(rc, where, self._lib.rt_cuda_multi_last_error(self._m).decode())
+
+    def close(self):
+        if self._m:
+            self._lib.rt_cuda_multi_destroy(self._m)
+            self._m = _P()
+
+    def __enter__(self):
+        return self
+
+    def __exit__(self, *a):
+        self.close()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def upload_scene(self, spheres: np.ndarray, lights: np.ndarray):
+        spheres = np.ascontiguousarray(spheres)
+        lights = np.ascontiguousarray(lights)
+        self._check(self._lib.rt_cuda_multi_upload_scene(
+            self._m, spheres.ctypes.data if len(spheres) else None, len(spheres),
+            lights.ctypes.data if len(lights) else None, len(lights)), "rt_cuda_multi_upload_scene")
+
+    def set_option(self, key: str, value: int):
+        self._check(self._lib.rt_cuda_multi_set_option(self._m, key.encode(), int(value)), "rt_cuda_multi_set_option")
+
+    def render(self, width, height, zoom=-4.0, alias=1.0, max_stack=6, strip_rows=0):
+        self._check(self._lib.rt_cuda_multi_render(self._m, width, height, zoom, alias, max_stack, strip_rows),
+                    "rt_cuda_multi_render")
+        self.width, self.height = width, height
+
+    def synchronize(self):
+        self._check(self._lib.rt_cuda_multi_synchronize(self._m), "rt_cuda_multi_synchronize")
+
+    def flush_l2(self):
+        self._check(self._lib.rt_cuda_multi_flush_l2(self._m), "rt_cuda_multi_flush_l2")
+
+    def readback_rgb8(self, local: int = 0, out: np.ndarray | None = None):
+        """-> (uint8 [H, W, 3] assembled frame, global max colour)"""
+        if out is None:
+            out = np.empty((self.height, self.width, 3), np.uint8)
+        mx = ctypes.c_float(0)
+        self._check(self._lib.rt_cuda_multi_readback_rgb8(self._m, local, out.ctypes.data, ctypes.byref(mx)),
+                    "rt_cuda_multi_readback_rgb8")
+        return out, mx.value
+
+    def readback_rgb8_async(self, out: "HostBuffer", local: int = 0):
+        self._check(self._lib.rt_cuda_multi_readback_rgb8_async(self._m, local, out.array.ctypes.data),
+                    "rt_cuda_multi_readback_rgb8_async")
+
+    def readback_wait(self, local: int = 0):
+        self._check(self._lib.rt_cuda_multi_readback_wait(self._m, local), "rt_cuda_multi_readback_wait")
+
+    def set_stream(self, cuda_stream: int, local: int = 0):
+        ctx = self._lib.rt_cuda_multi_context(self._m, local)
+        rc = _lib().rt_cuda_set_stream(_P(ctx), _P(cuda_stream))
+        if rc:
+            raise RtCudaError(rc, "rt_cuda_set_stream")
+
+    def step_ms(self, local: int = 0) -> float:
+        ms = ctypes.c_float(0)
+        self._check(self._lib.rt_cuda_multi_step_ms(self._m, local, ctypes.byref(ms)), "rt_cuda_multi_step_ms")
+        return ms.value
+
+    def device_frame(self, local: int = 0) -> int:
+        return int(self._lib.rt_cuda_multi_device_frame(self._m, local) or 0)
+
+    def stats(self, local: int = 0) -> dict:
+        ctx = self._lib.rt_cuda_multi_context(self._m, local)
+        s = Stats()
+        rc = _lib().rt_cuda_get_stats(_P(ctx), ctypes.byref(s))
+        if rc:
+            raise RtCudaError(rc, "rt_cuda_get_stats")
+        return s.as_dict()
 
 
 def write_ppm(path, rgb8: np.ndarray):

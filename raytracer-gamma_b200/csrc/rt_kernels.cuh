@@ -78,7 +78,11 @@ struct TraceParams {
   uint32_t list1Max;        /* accelerated mode: capacity of the per-lane (sub, cluster) lists */
 };
 
-__constant__ float4_ c_filt[RT_CONST_MAX_SPHERES];
+/* "__constant__ staging" (option staging=1): the filter records travel with the launch as a
+ * __grid_constant__ kernel parameter, i.e. in the constant bank the parameters live in (LDC with a
+ * warp-uniform index), so every launch reads ITS context's records — a module-global __constant__
+ * symbol would be shared by all contexts of a process. */
+struct ConstRecords { float4_ r[RT_CONST_MAX_SPHERES]; };
 
 /* ---- TMA bulk staging (global -> shared, completion on an mbarrier) --------- */
 __device__ __forceinline__ uint32_t smem_u32(const void* p) {
@@ -152,10 +156,10 @@ struct WarpCtx {
 };
 
 template <bool USE_CONST>
-__device__ __forceinline__ float4_ load_filt(const WarpCtx& w, uint32_t i) {
+__device__ __forceinline__ float4_ load_filt(const WarpCtx& w, const ConstRecords& cr, uint32_t i) {
   float4_ s;
   if (USE_CONST) {
-    s = c_filt[i];
+    s = cr.r[i];          /* cr IS the kernel's __grid_constant__ parameter: LDC with a warp-uniform index */
   } else {
     const float4 v = w.filt[i];
     s.x = v.x; s.y = v.y; s.z = v.z; s.w = v.w;
@@ -288,7 +292,7 @@ __device__ __noinline__ uint32_t exact_all(const SceneView sc, Slot* s, unsigned
 
 /* ---- trace pass: up to two rays per lane ---------------------------------------- */
 template <bool USE_CONST>
-__device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_trace(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
                                            int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_T;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
@@ -318,7 +322,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slo
       unsigned k = 0;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
         const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
         const f32x2 b = bq2(DD, cx, cy, cz);
         f32x2 ch = fma2(OO.px, cx, pk1(s.w));
@@ -363,7 +367,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, WarpCtx& w, Slo
  * A lane with no shadow batch waiting may bring a TRACE slot instead: a trace ray is the
  * same query with one direction, so it rides along for free and keeps the lane busy. */
 template <bool USE_CONST, int ND>
-__device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_shadow(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
                                             Counters& ctr) {
   constexpr int G = (ND == 4) ? RT_GROUP_S4 : RT_GROUP_S2;
   OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
@@ -422,7 +426,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Sl
       unsigned sk = 0u;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
         const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
         const f32x2 e = pk1(ex_sub(O.nq, filter_ch(O, s)));   /* -q - ch: once per sphere, all rays share the origin */
 #pragma unroll
@@ -474,7 +478,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, WarpCtx& w, Sl
 
 /* ---- containment pass: up to two probe points per lane ---------------------------- */
 template <bool USE_CONST>
-__device__ __forceinline__ void pass_contain(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_contain(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
                                              int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_C;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
@@ -493,7 +497,7 @@ __device__ __forceinline__ void pass_contain(const TraceParams& p, WarpCtx& w, S
       unsigned k = 0;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
         f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
         ch = fma2(OO.py, pk1(s.y), ch);
         ch = fma2(OO.pz, pk1(s.z), ch);
@@ -580,7 +584,7 @@ __device__ __forceinline__ void gather2(const WarpCtx& w, unsigned bits, uint32_
 }
 
 template <bool USE_CONST>
-__device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_trace_accel(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
                                                  int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_TA;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
@@ -614,7 +618,7 @@ __device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& 
       unsigned k = 0;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
         const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
         const f32x2 b = bq2(DD, cx, cy, cz);
         f32x2 ch = fma2(OO.px, cx, pk1(s.w));
@@ -671,7 +675,7 @@ __device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& 
 }
 
 template <bool USE_CONST, int ND>
-__device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
                                                   Counters& ctr) {
   constexpr int G = (ND == 4) ? RT_GROUP_S4A : RT_GROUP_S2;
   OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
@@ -733,7 +737,7 @@ __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx&
       unsigned sk = 0u;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
         const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
         const f32x2 e = pk1(ex_sub(OC.nq, filter_ch(OC, s)));
 #pragma unroll
@@ -797,7 +801,7 @@ __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx&
 }
 
 template <bool USE_CONST>
-__device__ __forceinline__ void pass_contain_accel(const TraceParams& p, WarpCtx& w, Slot* slots, int s0,
+__device__ __forceinline__ void pass_contain_accel(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
                                                    int s1, Counters& ctr) {
   constexpr int G = RT_GROUP_CA;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
@@ -821,7 +825,7 @@ __device__ __forceinline__ void pass_contain_accel(const TraceParams& p, WarpCtx
       unsigned k = 0;
 #pragma unroll
       for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, base + j);
+        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
         f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
         ch = fma2(OO.py, pk1(s.y), ch);
         ch = fma2(OO.pz, pk1(s.z), ch);
@@ -911,8 +915,8 @@ __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, Slot* slo
   return (uint32_t)s.kind | ((uint32_t)s.ndirs << 4);
 }
 
-template <bool USE_CONST, int MIN_BLOCKS, int NSLOTS, bool ACCEL = false>
-__global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const TraceParams p) {
+template <bool USE_CONST, int NSLOTS, bool ACCEL>
+__device__ __forceinline__ void trace_body(const TraceParams& p, const ConstRecords& cr) {
   static_assert(!(ACCEL && USE_CONST), "the accelerated mode stages its records in shared memory");
   extern __shared__ __align__(128) unsigned char smem_raw[];
   /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists][shadow-ray scratch];
@@ -1044,18 +1048,18 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
     }
     if (mode == K_SHADOW) {
       if (ndMax <= 2 && !(ACCEL && RT_ACCEL_ONE_SHADOW)) {
-        if (ACCEL) pass_shadow_accel<USE_CONST, 2>(p, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 2>(p, w, slots, sv0, ctr);
+        if (ACCEL) pass_shadow_accel<USE_CONST, 2>(p, cr, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 2>(p, cr, w, slots, sv0, ctr);
         passS2++;
       } else {
-        if (ACCEL) pass_shadow_accel<USE_CONST, 4>(p, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 4>(p, w, slots, sv0, ctr);
+        if (ACCEL) pass_shadow_accel<USE_CONST, 4>(p, cr, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 4>(p, cr, w, slots, sv0, ctr);
         passS4++;
       }
       if (s0 >= 0) servedS += (unsigned)nd; else servedT += (unsigned)ndS;
     } else if (mode == K_TRACE) {
-      if (ACCEL) pass_trace_accel<USE_CONST>(p, w, slots, t0, t1, ctr); else pass_trace<USE_CONST>(p, w, slots, t0, t1, ctr);
+      if (ACCEL) pass_trace_accel<USE_CONST>(p, cr, w, slots, t0, t1, ctr); else pass_trace<USE_CONST>(p, cr, w, slots, t0, t1, ctr);
       passT++; servedT += (unsigned)((t0 >= 0) + (t1 >= 0));
     } else {
-      if (ACCEL) pass_contain_accel<USE_CONST>(p, w, slots, c0, c1, ctr); else pass_contain<USE_CONST>(p, w, slots, c0, c1, ctr);
+      if (ACCEL) pass_contain_accel<USE_CONST>(p, cr, w, slots, c0, c1, ctr); else pass_contain<USE_CONST>(p, cr, w, slots, c0, c1, ctr);
       passC++; servedC += (unsigned)((c0 >= 0) + (c1 >= 0));
     }
     RT_TICK(3);
@@ -1112,6 +1116,18 @@ __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const Trace
   }
 }
 
+/* The two entry points: records staged in shared memory by TMA (every scene size, and the
+ * accelerated mode), or read from the launch's constant bank (<= RT_CONST_MAX_SPHERES records). */
+template <int MIN_BLOCKS, int NSLOTS, bool ACCEL>
+__global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams p) {
+  trace_body<false, NSLOTS, ACCEL>(p, *reinterpret_cast<const ConstRecords*>(0));   /* never read without USE_CONST */
+}
+template <int MIN_BLOCKS, int NSLOTS>
+__global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel_const(const __grid_constant__ TraceParams p,
+                                                                          const __grid_constant__ ConstRecords c) {
+  trace_body<true, NSLOTS, false>(p, c);
+}
+
 /* Sum each pixel's samples in the reference's order (main.cpp:430-447) and take the frame's
  * NaN-skipping maximum (algebra.h:68-91).  HBM-bound: 16 B x spp read + 16 B written per pixel. */
 __global__ void combine_kernel(const float4* __restrict__ samples, float4* __restrict__ fb, uint32_t npix,
@@ -1135,10 +1151,10 @@ __global__ void combine_kernel(const float4* __restrict__ samples, float4* __res
 
 /* float4 framebuffer -> packed 12-byte pixels (the reference's `Vec dst[]`, .cl:972) */
 __global__ void pack_kernel(const float4* __restrict__ fb, float* __restrict__ out, uint32_t npix) {
-  const uint32_t stride = gridDim.x * blockDim.x;
-  const uint32_t nflt = npix * 3u;
-  for (uint32_t i = blockIdx.x * blockDim.x + threadIdx.x; i < nflt; i += stride) {
-    const uint32_t px = i / 3u, c = i - px * 3u;
+  const size_t stride = (size_t)gridDim.x * blockDim.x;
+  const size_t nflt = (size_t)npix * 3u;
+  for (size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x; i < nflt; i += stride) {
+    const size_t px = i / 3u, c = i - px * 3u;
     const float* f = reinterpret_cast<const float*>(fb + px);
     out[i] = f[c];
   }

@@ -11,13 +11,16 @@
 
 #include "rt_cuda.h"
 #include "rt_kernels.cuh"
-#include "rt_wavefront.cuh"
 #include "rt_soa.h"
 
 using namespace rtg;
 
 #define RT_DEFAULT_MIN_BLOCKS 2
+#ifndef RT_DEFAULT_SLOTS
 #define RT_DEFAULT_SLOTS 4
+#endif
+#define RT_COPY_CHUNK (8u << 20)     /* pageable readback: D2H and the host memcpy alternate over two pinned chunks */
+#define RT_FLUSH_BYTES (256u << 20)  /* rt_cuda_flush_l2: larger than the 126 MB L2 */
 
 struct rt_cuda_ctx {
   int device = 0;
@@ -30,11 +33,15 @@ struct rt_cuda_ctx {
   char lastError[256] = {0};
 
   /* scene */
-  bool haveScene = false;
+  bool haveScene = false, haveClusters = false;
   uint32_t n = 0, nPad = 0, nl = 0;
-  float4_* dScene = nullptr;       /* one allocation: filt | geo | matA | matB | lpos | lcol */
+  float4_* dScene = nullptr;       /* one allocation: filt | geo | matA | matB | lpos | lcol | cluster form */
   size_t sceneCap = 0;
   SceneView view{};
+  SceneLayout layout{};
+  std::vector<rt_sphere> hSpheres; /* kept for the lazy build of the cluster form (option accel) */
+  std::vector<rt_light> hLights;
+  ConstRecords* hConst = nullptr;  /* padded filter records, handed to trace_kernel_const as a launch parameter */
 
   /* frame */
   bool haveFrame = false;
@@ -45,21 +52,27 @@ struct rt_cuda_ctx {
   unsigned char* dRgb8 = nullptr; size_t rgbCap = 0;
   unsigned int* dWork = nullptr;     /* [0] queue head, [1] max bits */
   unsigned long long* dCounters = nullptr;
-  void* hPinned = nullptr; size_t pinnedCap = 0;
+  void* dFlush = nullptr;
+
+  /* synchronous readback through two pinned chunks */
+  unsigned char* hChunk[2] = {nullptr, nullptr};
+  cudaEvent_t evChunk[2] = {nullptr, nullptr};
+
+  /* asynchronous readback: two frames in flight on a second stream */
+  cudaStream_t copyStream = nullptr;
+  struct Ticket {
+    unsigned char* dRgb = nullptr; size_t cap = 0;
+    cudaEvent_t evQuant = nullptr, evCopy = nullptr;
+    bool pending = false;
+    unsigned char* hStage = nullptr; size_t stageCap = 0;   /* used when the caller's buffer is not pinned */
+    unsigned char* userDst = nullptr; size_t bytes = 0;
+  } tk[2];
+  unsigned nextTicket = 0;
 
   /* options */
   int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0, slots = 0, prefetch = 0;
-  int engine = 0;                  /* 0 auto, 1 persistent kernel, 2 wavefront */
   int accel = 0;                   /* 1: two-level cluster filter (optional accelerated mode) */
   uint32_t nc = 0, ncPad = 0;
-  long pool = 0;                   /* wavefront: samples in flight (0 = default) */
-
-  /* wavefront pool */
-  uint32_t* dPool = nullptr; size_t poolCap = 0;      /* words */
-  Frame* dStacks = nullptr; size_t stacksCap = 0;     /* samples */
-  uint32_t* dQueues = nullptr; size_t queuesCap = 0;  /* entries */
-  uint32_t* dCounts = nullptr;                        /* [2][4] */
-  uint32_t* hCounts = nullptr;                        /* pinned [4] */
 
   /* stats */
   rt_cuda_stats stats{};
@@ -87,6 +100,7 @@ extern "C" const char* rt_cuda_strerror(int status) {
     case RT_CUDA_ERR_NO_FRAME: return "RT_CUDA_ERR_NO_FRAME";
     case RT_CUDA_ERR_TOO_LARGE: return "RT_CUDA_ERR_TOO_LARGE";
     case RT_CUDA_ERR_OUT_OF_MEMORY: return "RT_CUDA_ERR_OUT_OF_MEMORY";
+    case RT_CUDA_ERR_NCCL: return "RT_CUDA_ERR_NCCL";
     default: return "RT_CUDA_ERR_UNKNOWN";
   }
 }
@@ -134,7 +148,14 @@ extern "C" int rt_cuda_init(int device, rt_cuda_ctx** out) {
   ctx->smemOptin = (int)pr.sharedMemPerBlockOptin;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(RT_CUDA_ERR_CUDA);
   ctx->ownStream = true;
+  if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) return fail(RT_CUDA_ERR_CUDA);
   if (cudaEventCreate(&ctx->ev0) != cudaSuccess || cudaEventCreate(&ctx->ev1) != cudaSuccess) return fail(RT_CUDA_ERR_CUDA);
+  for (int i = 0; i < 2; ++i) {
+    if (cudaEventCreateWithFlags(&ctx->evChunk[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->tk[i].evQuant, cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->tk[i].evCopy, cudaEventDisableTiming) != cudaSuccess)
+      return fail(RT_CUDA_ERR_CUDA);
+  }
   if (cudaMalloc(&ctx->dWork, 4 * sizeof(unsigned int)) != cudaSuccess) return fail(RT_CUDA_ERR_OUT_OF_MEMORY);
   if (cudaMalloc(&ctx->dCounters, RT_NUM_COUNTERS * sizeof(unsigned long long)) != cudaSuccess) return fail(RT_CUDA_ERR_OUT_OF_MEMORY);
   cudaMemset(ctx->dWork, 0, 4 * sizeof(unsigned int));
@@ -147,15 +168,23 @@ extern "C" void rt_cuda_destroy(rt_cuda_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
+  if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
   cudaFree(ctx->dScene); cudaFree(ctx->dFb); cudaFree(ctx->dPacked); cudaFree(ctx->dRgb8); cudaFree(ctx->dSamples);
-  cudaFree(ctx->dPool); cudaFree(ctx->dStacks); cudaFree(ctx->dQueues); cudaFree(ctx->dCounts);
-  if (ctx->hCounts) cudaFreeHost(ctx->hCounts);
-  cudaFree(ctx->dWork); cudaFree(ctx->dCounters);
-  if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
+  cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->dFlush);
+  for (int i = 0; i < 2; ++i) {
+    if (ctx->hChunk[i]) cudaFreeHost(ctx->hChunk[i]);
+    if (ctx->evChunk[i]) cudaEventDestroy(ctx->evChunk[i]);
+    cudaFree(ctx->tk[i].dRgb);
+    if (ctx->tk[i].hStage) cudaFreeHost(ctx->tk[i].hStage);
+    if (ctx->tk[i].evQuant) cudaEventDestroy(ctx->tk[i].evQuant);
+    if (ctx->tk[i].evCopy) cudaEventDestroy(ctx->tk[i].evCopy);
+  }
   if (ctx->ev0) cudaEventDestroy(ctx->ev0);
   if (ctx->ev1) cudaEventDestroy(ctx->ev1);
+  if (ctx->copyStream) cudaStreamDestroy(ctx->copyStream);
   if (ctx->ownStream && ctx->stream) cudaStreamDestroy(ctx->stream);
   cudaGetLastError();
+  delete ctx->hConst;
   delete ctx;
 }
 
@@ -169,6 +198,9 @@ extern "C" int rt_cuda_set_stream(rt_cuda_ctx* ctx, void* s) {
   return RT_CUDA_OK;
 }
 
+extern "C" void* rt_cuda_get_stream(rt_cuda_ctx* ctx) { return ctx ? (void*)ctx->stream : nullptr; }
+extern "C" int rt_cuda_get_device(rt_cuda_ctx* ctx) { return ctx ? ctx->device : -1; }
+
 extern "C" int rt_cuda_synchronize(rt_cuda_ctx* ctx) {
   if (!ctx) return RT_CUDA_ERR_INVALID_ARG;
   CU(cudaSetDevice(ctx->device));
@@ -181,13 +213,40 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!strcmp(key, "staging")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->staging = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
   if (!strcmp(key, "accel")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->accel = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "engine")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->engine = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "pool")) { if (value < 0) return RT_CUDA_ERR_INVALID_ARG; ctx->pool = value; return RT_CUDA_OK; }
+  if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
+#ifdef RT_DEV_VARIANTS   /* development builds only: register-budget / slot-count variants of the trace kernel */
   if (!strcmp(key, "prefetch")) { ctx->prefetch = value ? 1 : 0; return RT_CUDA_OK; }
   if (!strcmp(key, "slots")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->slots = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "min_blocks")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->minBlocks = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "min_blocks")) { if (value != 0 && (value < 2 || value > 3)) return RT_CUDA_ERR_INVALID_ARG; ctx->minBlocks = (int)value; return RT_CUDA_OK; }
+#endif
   return RT_CUDA_ERR_INVALID_ARG;
+}
+
+/* (Re)build the device scene from the context's host copy; `withClusters` adds the two-level form. */
+static int push_scene(rt_cuda_ctx* ctx, bool withClusters) {
+  std::vector<float4_> h;
+  SceneLayout lay;
+  build_scene_soa(ctx->hSpheres.data(), (uint32_t)ctx->hSpheres.size(), ctx->hLights.data(),
+                  (uint32_t)ctx->hLights.size(), h, lay, withClusters);
+  if (lay.total > ctx->sceneCap) {
+    CU(cudaStreamSynchronize(ctx->stream));
+    cudaFree(ctx->dScene); ctx->dScene = nullptr; ctx->sceneCap = 0;
+    CU(cudaMalloc(&ctx->dScene, lay.total * sizeof(float4_)));
+    ctx->sceneCap = lay.total;
+  }
+  CU(cudaMemcpyAsync(ctx->dScene, h.data(), lay.total * sizeof(float4_), cudaMemcpyHostToDevice, ctx->stream));
+  if (lay.n && lay.nPad <= RT_CONST_MAX_SPHERES) {
+    if (!ctx->hConst) ctx->hConst = new (std::nothrow) ConstRecords();
+    if (!ctx->hConst) return RT_CUDA_ERR_OUT_OF_MEMORY;
+    memcpy(ctx->hConst->r, h.data() + lay.offFilt, (size_t)lay.nPad * sizeof(float4_));
+    for (uint32_t i = lay.nPad; i < RT_CONST_MAX_SPHERES; ++i) ctx->hConst->r[i] = float4_{0.f, 0.f, 0.f, INFINITY};
+  }
+  CU(cudaStreamSynchronize(ctx->stream));   /* h goes out of scope */
+  ctx->layout = lay;
+  ctx->view = scene_view(ctx->dScene, lay);
+  ctx->n = lay.n; ctx->nPad = lay.nPad; ctx->nl = lay.nl; ctx->nc = lay.nc; ctx->ncPad = lay.ncPad;
+  ctx->haveClusters = withClusters;
+  return RT_CUDA_OK;
 }
 
 extern "C" int rt_cuda_upload_scene(rt_cuda_ctx* ctx, const rt_sphere* spheres, unsigned sphNum,
@@ -196,127 +255,29 @@ extern "C" int rt_cuda_upload_scene(rt_cuda_ctx* ctx, const rt_sphere* spheres, 
   if ((sphNum && !spheres) || (lgtNum && !lights)) return RT_CUDA_ERR_INVALID_ARG;
   if (sphNum > RT_CUDA_MAX_SPHERES) return RT_CUDA_ERR_TOO_LARGE;
   CU(cudaSetDevice(ctx->device));
-  std::vector<float4_> h;
-  SceneLayout lay;
-  build_scene_soa(spheres, sphNum, lights, lgtNum, h, lay);
-
-  if (lay.total > ctx->sceneCap) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dScene); ctx->dScene = nullptr; ctx->sceneCap = 0;
-    CU(cudaMalloc(&ctx->dScene, lay.total * sizeof(float4_)));
-    ctx->sceneCap = lay.total;
-  }
-  CU(cudaMemcpyAsync(ctx->dScene, h.data(), lay.total * sizeof(float4_), cudaMemcpyHostToDevice, ctx->stream));
-  if (lay.n && lay.nPad <= RT_CONST_MAX_SPHERES)
-    CU(cudaMemcpyToSymbolAsync(c_filt, h.data() + lay.offFilt, (size_t)lay.nPad * sizeof(float4_), 0,
-                               cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));   /* h goes out of scope */
-
-  ctx->view = scene_view(ctx->dScene, lay);
-  ctx->n = lay.n; ctx->nPad = lay.nPad; ctx->nl = lay.nl; ctx->nc = lay.nc; ctx->ncPad = lay.ncPad;
+  ctx->haveScene = false;
+  ctx->hSpheres.assign(spheres, spheres + sphNum);
+  ctx->hLights.assign(lights, lights + lgtNum);
+  /* the cluster form is only built when the accelerated mode is (or later becomes) selected */
+  int rc = push_scene(ctx, ctx->accel != 0);
+  if (rc) return rc;
   ctx->haveScene = true;
   return RT_CUDA_OK;
 }
 
-static int ensure_frame(rt_cuda_ctx* ctx, size_t pixels) {
-  if (pixels > ctx->fbCap) {
+/* grow-only device buffer */
+template <typename T>
+static int ensure_dev(rt_cuda_ctx* ctx, T*& ptr, size_t& cap, size_t need) {
+  if (need > cap) {
     CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dFb); ctx->dFb = nullptr; ctx->fbCap = 0;
-    CU(cudaMalloc(&ctx->dFb, pixels * sizeof(float4)));
-    ctx->fbCap = pixels;
+    cudaFree(ptr); ptr = nullptr; cap = 0;
+    CU(cudaMalloc(&ptr, need * sizeof(T)));
+    cap = need;
   }
   return RT_CUDA_OK;
 }
 
-#define RT_ACCEL_MIN_SPHERES 768u           /* accel = 1 engages from here (6 % slower at 512, 25 % faster at 1024: profiles/r1/sweep_config5.jsonl); accel = 2 forces it */
-#define RT_DEFAULT_POOL (1l << 21)          /* samples in flight of the wavefront engine */
-
-/* The wavefront engine: alternate the pure filter kernels and the shade kernel over a pool
- * of samples until the frame's work counter and all queues are drained (rt_wavefront.cuh).
- * The host only launches; it looks at the queue lengths every few rounds to know when to stop. */
-static int render_wavefront(rt_cuda_ctx* ctx, const TraceParams& tp, uint32_t spp, size_t pixels) {
-  const uint64_t totalWork = (uint64_t)pixels * spp;
-  if (totalWork >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
-  uint64_t P = (uint64_t)(ctx->pool > 0 ? ctx->pool : RT_DEFAULT_POOL);
-  if (P > totalWork) P = totalWork;
-  if (P * RT_SLOT_WORDS > ctx->poolCap) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dPool); ctx->dPool = nullptr; ctx->poolCap = 0;
-    CU(cudaMalloc(&ctx->dPool, P * RT_SLOT_WORDS * sizeof(uint32_t)));
-    ctx->poolCap = P * RT_SLOT_WORDS;
-  }
-  if (P > ctx->stacksCap) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dStacks); ctx->dStacks = nullptr; ctx->stacksCap = 0;
-    CU(cudaMalloc(&ctx->dStacks, P * RT_MAX_STACK * sizeof(Frame)));
-    ctx->stacksCap = P;
-  }
-  if (P * 6 > ctx->queuesCap) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dQueues); ctx->dQueues = nullptr; ctx->queuesCap = 0;
-    CU(cudaMalloc(&ctx->dQueues, P * 6 * sizeof(uint32_t)));
-    ctx->queuesCap = P * 6;
-  }
-  if (!ctx->dCounts) CU(cudaMalloc(&ctx->dCounts, 8 * sizeof(uint32_t)));
-  if (!ctx->hCounts) CU(cudaMallocHost(&ctx->hCounts, 4 * sizeof(uint32_t)));
-
-  WfParams wp;
-  wp.sc = tp.sc; wp.cam = tp.cam;
-  wp.st = ctx->dPool; wp.stacks = ctx->dStacks; wp.queues = ctx->dQueues; wp.counts = ctx->dCounts;
-  wp.P = (uint32_t)P; wp.cur = 0;
-  wp.fb = tp.fb; wp.samples = tp.samples; wp.spp = spp;
-  wp.workCounter = tp.workCounter; wp.maxBits = tp.maxBits; wp.counters = tp.counters;
-  wp.localRows = tp.localRows; wp.stripRows = tp.stripRows; wp.stripFirst = tp.stripFirst; wp.stripStride = tp.stripStride;
-  wp.totalWork = (uint32_t)totalWork;
-  wp.noFilter = tp.noFilter;
-
-  const size_t smem = 16 + (size_t)ctx->nPad * 16 + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
-                      + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
-  CU(cudaFuncSetAttribute(wf_filter<K_TRACE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaFuncSetAttribute(wf_filter<K_SHADOW>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  CU(cudaFuncSetAttribute(wf_filter<K_CONTAIN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSM = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, wf_filter<K_SHADOW>, RT_BLOCK, smem));
-  if (perSM < 1) return RT_CUDA_ERR_TOO_LARGE;
-  const uint32_t gridF = (uint32_t)ctx->smCount * (uint32_t)perSM;
-  const uint32_t gridS = (uint32_t)ctx->smCount * 16u;
-
-  /* the first P work items are handed out by wf_spawn; the work counter continues from P */
-  const uint32_t init[8] = {(uint32_t)P, 0, 0, 0, 0, 0, 0, 0};
-  CU(cudaMemcpyAsync(ctx->dCounts, init, sizeof init, cudaMemcpyHostToDevice, ctx->stream));
-  const uint32_t first = (uint32_t)P;
-  CU(cudaMemcpyAsync(tp.workCounter, &first, sizeof first, cudaMemcpyHostToDevice, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));          /* `init` / `first` are stack variables */
-
-  CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  wf_spawn<<<(uint32_t)((P + 255) / 256), 256, 0, ctx->stream>>>(wp);
-  CU(cudaGetLastError());
-  ctx->launches += 1;
-  const int CHECK = 4;
-  for (int round = 1;; ++round) {
-    wf_filter<K_TRACE><<<gridF, RT_BLOCK, smem, ctx->stream>>>(wp);
-    wf_filter<K_SHADOW><<<gridF, RT_BLOCK, smem, ctx->stream>>>(wp);
-    wf_filter<K_CONTAIN><<<gridF, RT_BLOCK, smem, ctx->stream>>>(wp);
-    CU(cudaMemsetAsync(ctx->dCounts + (wp.cur ^ 1u) * 4u, 0, 4 * sizeof(uint32_t), ctx->stream));
-    wf_shade<<<gridS, 128, 0, ctx->stream>>>(wp, K_TRACE);
-    wf_shade<<<gridS, 128, 0, ctx->stream>>>(wp, K_SHADOW);
-    wf_shade<<<gridS, 128, 0, ctx->stream>>>(wp, K_CONTAIN);
-    CU(cudaGetLastError());
-    ctx->launches += 6;
-    wp.cur ^= 1u;
-    if (round % CHECK == 0) {
-      CU(cudaMemcpyAsync(ctx->hCounts, ctx->dCounts + wp.cur * 4u, 4 * sizeof(uint32_t), cudaMemcpyDeviceToHost, ctx->stream));
-      CU(cudaStreamSynchronize(ctx->stream));
-      if ((ctx->hCounts[0] | ctx->hCounts[1] | ctx->hCounts[2]) == 0u) break;
-    }
-    if (round > (1 << 22)) return RT_CUDA_ERR_CUDA;   /* cannot happen: every round retires work */
-  }
-  CU(cudaEventRecord(ctx->ev1, ctx->stream));
-  ctx->timed = true;
-  ctx->stats.grid = gridF; ctx->stats.block = RT_BLOCK; ctx->stats.smem_bytes = (uint32_t)smem;
-  ctx->stats.staging = 2;
-  return RT_CUDA_OK;
-}
+#define RT_ACCEL_MIN_SPHERES 768u           /* accel = 1 engages from here; accel = 2 forces it */
 
 extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned height, float zoom,
                                      float aliasFactor, int maxStack, unsigned stripRows,
@@ -328,7 +289,7 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if ((uint64_t)width * height >= (1ull << 31)) return RT_CUDA_ERR_TOO_LARGE;
   CU(cudaSetDevice(ctx->device));
 
-  /* rows owned by this shard */
+  /* ---- everything that can fail is computed and allocated before the context is touched ---- */
   const uint32_t nStrips = (height + stripRows - 1) / stripRows;
   uint32_t localRows = 0;
   for (uint32_t s = stripFirst; s < nStrips; s += stripStride) {
@@ -336,116 +297,118 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
     const uint32_t r1 = (r0 + stripRows < height) ? r0 + stripRows : height;
     localRows += r1 - r0;
   }
-  ctx->W = width; ctx->H = height; ctx->localRows = localRows;
-  ctx->launches = 0;
-  ctx->timed = false;
   const size_t pixels = (size_t)localRows * width;
-  int rc = ensure_frame(ctx, pixels ? pixels : 1);
-  if (rc) return rc;
-
-  CU(cudaMemsetAsync(ctx->dWork, 0, 4 * sizeof(unsigned int), ctx->stream));
-  CU(cudaMemsetAsync(ctx->dCounters, 0, RT_NUM_COUNTERS * sizeof(unsigned long long), ctx->stream));
-  ctx->haveFrame = true;
-  memset(&ctx->stats, 0, sizeof ctx->stats);
-  if (pixels == 0) return RT_CUDA_OK;
 
   TraceParams p;
-  p.sc = ctx->view;
   p.cam = make_camera(width, height, zoom, aliasFactor, maxStack, (int)ctx->n);
+  if (p.cam.nIter >= (1 << 20)) return RT_CUDA_ERR_TOO_LARGE;          /* make_camera's cap: alias too large to iterate */
+  const uint64_t spp64 = (uint64_t)p.cam.nIter * (uint64_t)p.cam.nIter;
+  p.tilesX = (width + 7u) / 8u;
+  const uint32_t tilesY = (localRows + 3u) / 4u;
+  if (spp64 >= (1ull << 32) || (uint64_t)p.tilesX * tilesY * 32u * spp64 >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
+  const uint32_t spp = (uint32_t)spp64;
+
+  /* the accelerated mode needs something to cull, its records in shared memory, and the cluster form */
+  const size_t perCta = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short) + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float) + 16;
+  const uint32_t list1Max = (ctx->n >= 2048u) ? RT_LIST1_LARGE : RT_LIST1_SMALL;
+  const bool wantAccel = ctx->accel && !ctx->noFilter && ctx->n >= (ctx->accel == 2 ? 4u * RT_CLUSTER : RT_ACCEL_MIN_SPHERES);
+  if (wantAccel && !ctx->haveClusters) {       /* option set after the upload: add the cluster form now */
+    int rc = push_scene(ctx, true);
+    if (rc) return rc;
+  }
+  const size_t accelBytes = (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) + (size_t)list1Max * RT_BLOCK * sizeof(unsigned short);
+  /* ... and falls back to the plain mode when they do not fit one CTA (> ~8 000 spheres) */
+  const bool accel = wantAccel && ctx->haveClusters && perCta + accelBytes <= (size_t)ctx->smemOptin;
+
+  /* staging: shared memory filled by TMA bulk copies is the default at every size (it is equal or faster
+   * than the constant bank from 16 spheres up, profiles/r1/sweep_config5.jsonl); option staging=1 selects
+   * the constant-bank path for scenes of <= RT_CONST_MAX_SPHERES records */
+  int staging = ctx->staging;
+  if (staging == 0) staging = 2;
+  if (staging == 1 && (ctx->n == 0 || ctx->nPad > RT_CONST_MAX_SPHERES || !ctx->hConst)) staging = 2;
+  if (accel) staging = 2;
+  const bool useConst = (staging == 1);
+  const size_t sceneBytes = useConst ? 0 : accel ? (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) : (size_t)ctx->nPad * 16;
+  const size_t smem = 16 + sceneBytes + (accel ? (size_t)list1Max * RT_BLOCK * sizeof(unsigned short) : 0)
+                      + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
+                      + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
+
+  void (*kern)(const TraceParams) = nullptr;
+  void (*kernC)(const TraceParams, const ConstRecords) = nullptr;
+#ifdef RT_DEV_VARIANTS
+  const int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
+  const int nslots = ctx->slots ? ctx->slots : RT_DEFAULT_SLOTS;
+#define RT_PICK(M) ((nslots == 2) ? trace_kernel<M, 2, false> : (nslots == 3) ? trace_kernel<M, 3, false> : trace_kernel<M, 4, false>)
+#define RT_PICKC(M) ((nslots == 2) ? trace_kernel_const<M, 2> : (nslots == 3) ? trace_kernel_const<M, 3> : trace_kernel_const<M, 4>)
+  if (useConst) kernC = (minBlocks == 2) ? RT_PICKC(2) : RT_PICKC(3);
+  else          kern = (minBlocks == 2) ? RT_PICK(2) : RT_PICK(3);
+#undef RT_PICK
+#undef RT_PICKC
+#else
+  if (useConst) kernC = trace_kernel_const<RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS>;
+  else          kern = trace_kernel<RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS, false>;
+#endif
+  if (accel) { kern = trace_kernel<RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS, true>; kernC = nullptr; }
+  const void* kfn = kernC ? (const void*)kernC : (const void*)kern;
+  int perSM = 0;
+  uint32_t grid = 0, totalWork = 0;
+  if (pixels && spp) {
+    CU(cudaFuncSetAttribute(kfn, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, RT_BLOCK, smem));
+    if (perSM < 1) return RT_CUDA_ERR_TOO_LARGE;
+    if (ctx->blocksPerSM > 0 && ctx->blocksPerSM < perSM) perSM = ctx->blocksPerSM;
+    totalWork = p.tilesX * tilesY * 32u * spp;
+    grid = (uint32_t)ctx->smCount * (uint32_t)perSM;
+    const uint32_t needBlocks = (totalWork + RT_BLOCK - 1) / RT_BLOCK;
+    if (grid > needBlocks) grid = needBlocks;
+    if (grid < 1) grid = 1;
+  }
+  int rc = ensure_dev(ctx, ctx->dFb, ctx->fbCap, pixels ? pixels : 1);
+  if (rc) { ctx->haveFrame = false; return rc; }
+  if (spp > 1 && pixels) {
+    rc = ensure_dev(ctx, ctx->dSamples, ctx->samplesCap, pixels * spp);
+    if (rc) { ctx->haveFrame = false; return rc; }
+  }
+
+  /* ---- publish and launch ---- */
+  ctx->haveFrame = false;
+  ctx->launches = 0;
+  ctx->timed = false;
+  memset(&ctx->stats, 0, sizeof ctx->stats);
+  CU(cudaMemsetAsync(ctx->dWork, 0, 4 * sizeof(unsigned int), ctx->stream));
+  CU(cudaMemsetAsync(ctx->dCounters, 0, RT_NUM_COUNTERS * sizeof(unsigned long long), ctx->stream));
+  ctx->W = width; ctx->H = height; ctx->localRows = localRows;
+  ctx->stats.engine = 1;
+  if (pixels == 0) { ctx->haveFrame = true; return RT_CUDA_OK; }
+  if (spp == 0) {          /* alias <= 0: the sample loops never run, the frame is black (main.cpp:420) */
+    CU(cudaMemsetAsync(ctx->dFb, 0, pixels * sizeof(float4), ctx->stream));
+    ctx->haveFrame = true;
+    return RT_CUDA_OK;
+  }
+
+  p.sc = ctx->view;
   p.fb = ctx->dFb;
   p.workCounter = ctx->dWork;
   p.maxBits = ctx->dWork + 1;
   p.counters = ctx->dCounters;
   p.localRows = localRows;
   p.stripRows = stripRows; p.stripFirst = stripFirst; p.stripStride = stripStride;
-  /* work item = one sample of one pixel; samples are summed in order by combine_kernel */
-  const uint32_t spp = (uint32_t)p.cam.nIter * (uint32_t)p.cam.nIter;
-  if (spp == 0) {          /* alias <= 0: the sample loops never run, the frame is black (main.cpp:420) */
-    CU(cudaMemsetAsync(ctx->dFb, 0, pixels * sizeof(float4), ctx->stream));
-    return RT_CUDA_OK;
-  }
-  p.tilesX = (width + 7u) / 8u;
-  const uint32_t tilesY = (localRows + 3u) / 4u;
-  if ((uint64_t)p.tilesX * tilesY * 32u * spp >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
-  p.totalWork = p.tilesX * tilesY * 32u * spp;
+  p.totalWork = totalWork;
   p.spp = spp;
-  p.samples = nullptr;
-  if (spp > 1) {
-    const size_t need = pixels * spp;
-    if (need > ctx->samplesCap) {
-      CU(cudaStreamSynchronize(ctx->stream));
-      cudaFree(ctx->dSamples); ctx->dSamples = nullptr; ctx->samplesCap = 0;
-      CU(cudaMalloc(&ctx->dSamples, need * sizeof(float4)));
-      ctx->samplesCap = need;
-    }
-    p.samples = ctx->dSamples;
-  }
+  p.samples = (spp > 1) ? ctx->dSamples : nullptr;
   p.noFilter = ctx->noFilter;
   p.prefetch = ctx->prefetch;
-
-  /* engine choice: the wavefront engine (separate filter / shade kernels) is opt-in */
-  int engine = ctx->engine;
-  if (engine == 0) engine = 1;    /* the persistent kernel is faster at every size measured */
-  if (engine == 2 && ctx->n > 0) {
-    int rc = render_wavefront(ctx, p, spp, pixels);
-    if (rc) return rc;
-    ctx->stats.engine = 2;
-    if (spp > 1) {
-      combine_kernel<<<ctx->smCount * 8, 256, 0, ctx->stream>>>(ctx->dSamples, ctx->dFb, (uint32_t)pixels, spp, ctx->dWork + 1);
-      CU(cudaGetLastError());
-      ctx->launches += 1;
-    }
-    return RT_CUDA_OK;
-  }
-  ctx->stats.engine = 1;
-
-  /* staging choice: __constant__ broadcast for small scenes, shared memory (TMA bulk) otherwise */
-  int staging = ctx->staging;
-  if (staging == 0) staging = (ctx->n > 0 && ctx->nPad <= 64) ? 1 : 2;
-  if (staging == 1 && (ctx->n == 0 || ctx->nPad > RT_CONST_MAX_SPHERES)) staging = 2;
-  /* the accelerated mode needs something to cull and its records in shared memory */
-  const size_t perCta = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short) + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float) + 16;
-  const uint32_t list1Max = (ctx->n >= 2048u) ? RT_LIST1_LARGE : RT_LIST1_SMALL;
-  const size_t accelBytes = (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) + (size_t)list1Max * RT_BLOCK * sizeof(unsigned short);
-  /* ... and falls back to the plain mode when they do not fit one CTA (> ~8 000 spheres) */
-  const bool accel = ctx->accel && !ctx->noFilter && ctx->n >= (ctx->accel == 2 ? 4u * RT_CLUSTER : RT_ACCEL_MIN_SPHERES) &&
-                     perCta + accelBytes <= (size_t)ctx->smemOptin;
-  if (accel) staging = 2;
-  const bool useConst = (staging == 1);
-  const size_t sceneBytes = useConst ? 0 : accel ? (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) : (size_t)ctx->nPad * 16;
   p.list1Max = list1Max;
-  const size_t smem = 16 + sceneBytes + (accel ? (size_t)list1Max * RT_BLOCK * sizeof(unsigned short) : 0)
-                      + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
-                      + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
-  /* variants: MIN_BLOCKS resident CTAs per SM (register budget), NSLOTS pixels in flight per lane */
-  const int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
-  const int nslots = ctx->slots ? ctx->slots : RT_DEFAULT_SLOTS;
-  void (*kern)(const TraceParams) = nullptr;
-#define RT_PICK(C, M) ((nslots == 2) ? trace_kernel<C, M, 2> : (nslots == 3) ? trace_kernel<C, M, 3> : trace_kernel<C, M, 4>)
-  if (useConst) kern = (minBlocks == 2) ? RT_PICK(true, 2) : (minBlocks == 3) ? RT_PICK(true, 3) : RT_PICK(true, 4);
-  else          kern = (minBlocks == 2) ? RT_PICK(false, 2) : (minBlocks == 3) ? RT_PICK(false, 3) : RT_PICK(false, 4);
-#undef RT_PICK
-  if (accel) kern = trace_kernel<false, RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS, true>;
-  ctx->stats.accel = accel ? 1u : 0u;
-  ctx->stats.clusters = accel ? ctx->nc : 0u;
-  CU(cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  int perSM = 0;
-  CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kern, RT_BLOCK, smem));
-  if (perSM < 1) return RT_CUDA_ERR_TOO_LARGE;
-  if (ctx->blocksPerSM > 0 && ctx->blocksPerSM < perSM) perSM = ctx->blocksPerSM;
-  uint32_t grid = (uint32_t)ctx->smCount * (uint32_t)perSM;
-  const uint32_t needBlocks = (p.totalWork + RT_BLOCK - 1) / RT_BLOCK;
-  if (grid > needBlocks) grid = needBlocks;
-  if (grid < 1) grid = 1;
   /* queue granule: small enough to balance the tail, large enough to amortise the atomic */
   const uint32_t warps = grid * (RT_BLOCK / 32);
-  uint32_t chunk = (p.totalWork / (warps * 16u)) & ~31u;
+  uint32_t chunk = (totalWork / (warps * 16u)) & ~31u;
   if (chunk < 32u) chunk = 32u;
   if (chunk > 256u) chunk = 256u;
   p.chunk = chunk;
 
   CU(cudaEventRecord(ctx->ev0, ctx->stream));
-  kern<<<grid, RT_BLOCK, smem, ctx->stream>>>(p);
+  if (kernC) kernC<<<grid, RT_BLOCK, smem, ctx->stream>>>(p, *ctx->hConst);
+  else       kern<<<grid, RT_BLOCK, smem, ctx->stream>>>(p);
   CU(cudaGetLastError());
   CU(cudaEventRecord(ctx->ev1, ctx->stream));
   ctx->timed = true;
@@ -455,8 +418,11 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
     CU(cudaGetLastError());
     ctx->launches += 1;
   }
+  ctx->stats.accel = accel ? 1u : 0u;
+  ctx->stats.clusters = accel ? ctx->nc : 0u;
   ctx->stats.grid = grid; ctx->stats.block = RT_BLOCK; ctx->stats.smem_bytes = (uint32_t)smem;
   ctx->stats.staging = (uint32_t)staging;
+  ctx->haveFrame = true;
   return RT_CUDA_OK;
 }
 
@@ -466,30 +432,26 @@ extern "C" int rt_cuda_render(rt_cuda_ctx* ctx, unsigned width, unsigned height,
                                height ? height : 1, 0, 1);
 }
 
-static int ensure_pinned(rt_cuda_ctx* ctx, size_t bytes) {
-  if (bytes > ctx->pinnedCap) {
-    if (ctx->hPinned) cudaFreeHost(ctx->hPinned);
-    ctx->hPinned = nullptr; ctx->pinnedCap = 0;
-    CU(cudaMallocHost(&ctx->hPinned, bytes));
-    ctx->pinnedCap = bytes;
-  }
-  return RT_CUDA_OK;
-}
-
 extern "C" int rt_cuda_pack(rt_cuda_ctx* ctx) {
   if (!ctx) return RT_CUDA_ERR_INVALID_ARG;
   if (!ctx->haveFrame) return RT_CUDA_ERR_NO_FRAME;
   CU(cudaSetDevice(ctx->device));
   const size_t pixels = (size_t)ctx->localRows * ctx->W;
   if (pixels == 0) return RT_CUDA_OK;
-  if (pixels * 3 > ctx->packedCap) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dPacked); ctx->dPacked = nullptr; ctx->packedCap = 0;
-    CU(cudaMalloc(&ctx->dPacked, pixels * 3 * sizeof(float)));
-    ctx->packedCap = pixels * 3;
-  }
+  int rc = ensure_dev(ctx, ctx->dPacked, ctx->packedCap, pixels * 3);
+  if (rc) return rc;
   const int grid = ctx->smCount * 8;
   pack_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dFb, ctx->dPacked, (uint32_t)pixels);
+  CU(cudaGetLastError());
+  ctx->launches += 1;
+  return RT_CUDA_OK;
+}
+
+static int quantise_into(rt_cuda_ctx* ctx, void* devDst, float maxColour, cudaStream_t stream) {
+  const size_t pixels = (size_t)ctx->localRows * ctx->W;
+  const int grid = ctx->smCount * 8;
+  quantise_kernel<<<grid, 256, 0, stream>>>(ctx->dFb, reinterpret_cast<uint32_t*>(devDst),
+                                            (uint32_t)pixels, ctx->dWork + 1, maxColour);
   CU(cudaGetLastError());
   ctx->launches += 1;
   return RT_CUDA_OK;
@@ -501,33 +463,62 @@ extern "C" int rt_cuda_quantise(rt_cuda_ctx* ctx, float maxColour) {
   CU(cudaSetDevice(ctx->device));
   const size_t pixels = (size_t)ctx->localRows * ctx->W;
   if (pixels == 0) return RT_CUDA_OK;
-  const size_t bytes = ((pixels + 3) / 4) * 12;
-  if (bytes > ctx->rgbCap) {
-    CU(cudaStreamSynchronize(ctx->stream));
-    cudaFree(ctx->dRgb8); ctx->dRgb8 = nullptr; ctx->rgbCap = 0;
-    CU(cudaMalloc(&ctx->dRgb8, bytes));
-    ctx->rgbCap = bytes;
-  }
-  const int grid = ctx->smCount * 8;
-  quantise_kernel<<<grid, 256, 0, ctx->stream>>>(ctx->dFb, reinterpret_cast<uint32_t*>(ctx->dRgb8),
-                                                 (uint32_t)pixels, ctx->dWork + 1, maxColour);
-  CU(cudaGetLastError());
-  ctx->launches += 1;
-  return RT_CUDA_OK;
+  int rc = ensure_dev(ctx, ctx->dRgb8, ctx->rgbCap, ((pixels + 3) / 4) * 12);
+  if (rc) return rc;
+  return quantise_into(ctx, ctx->dRgb8, maxColour, ctx->stream);
+}
+
+extern "C" int rt_cuda_quantise_to(rt_cuda_ctx* ctx, void* devDst, size_t dstBytes, float maxColour) {
+  if (!ctx || !devDst) return RT_CUDA_ERR_INVALID_ARG;
+  if (!ctx->haveFrame) return RT_CUDA_ERR_NO_FRAME;
+  const size_t pixels = (size_t)ctx->localRows * ctx->W;
+  if (pixels == 0) return RT_CUDA_OK;
+  /* the kernel stores whole 32-bit words when four pixels are complete and single bytes for the rest */
+  if (dstBytes < pixels * 3 || ((uintptr_t)devDst & 3u)) return RT_CUDA_ERR_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  return quantise_into(ctx, devDst, maxColour, ctx->stream);
 }
 
 extern "C" void* rt_cuda_device_packed(rt_cuda_ctx* ctx) { return ctx ? (void*)ctx->dPacked : nullptr; }
 extern "C" void* rt_cuda_device_rgb8(rt_cuda_ctx* ctx) { return ctx ? (void*)ctx->dRgb8 : nullptr; }
 extern "C" void* rt_cuda_device_max(rt_cuda_ctx* ctx) { return ctx ? (void*)(ctx->dWork + 1) : nullptr; }
 
-/* Copy through the context's pinned staging buffer so the transfer runs at full PCIe rate
- * whatever memory the caller handed us. */
+extern "C" void* rt_cuda_host_alloc(size_t bytes) {
+  void* p = nullptr;
+  if (cudaHostAlloc(&p, bytes ? bytes : 1, cudaHostAllocDefault) != cudaSuccess) { cudaGetLastError(); return nullptr; }
+  return p;
+}
+extern "C" void rt_cuda_host_free(void* p) { if (p) { cudaFreeHost(p); cudaGetLastError(); } }
+
+static bool is_pinned(const void* p) {
+  cudaPointerAttributes a;
+  if (cudaPointerGetAttributes(&a, p) != cudaSuccess) { cudaGetLastError(); return false; }
+  return a.type == cudaMemoryTypeHost;
+}
+
+/* Device -> caller memory.  A pinned destination (rt_cuda_host_alloc, cudaHostRegister) takes one DMA;
+ * pageable memory goes through two pinned chunks so the DMA of chunk i+1 runs while the CPU copies chunk i. */
 static int copy_out(rt_cuda_ctx* ctx, void* dst, const void* dsrc, size_t bytes) {
-  int rc = ensure_pinned(ctx, bytes);
-  if (rc) return rc;
-  CU(cudaMemcpyAsync(ctx->hPinned, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  CU(cudaStreamSynchronize(ctx->stream));
-  memcpy(dst, ctx->hPinned, bytes);
+  if (is_pinned(dst)) {
+    CU(cudaMemcpyAsync(dst, dsrc, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+    CU(cudaStreamSynchronize(ctx->stream));
+    return RT_CUDA_OK;
+  }
+  for (int i = 0; i < 2; ++i)
+    if (!ctx->hChunk[i]) CU(cudaMallocHost(&ctx->hChunk[i], RT_COPY_CHUNK));
+  const size_t nChunks = (bytes + RT_COPY_CHUNK - 1) / RT_COPY_CHUNK;
+  for (size_t c = 0; c <= nChunks; ++c) {
+    if (c < nChunks) {
+      const size_t off = c * (size_t)RT_COPY_CHUNK, n = (bytes - off < RT_COPY_CHUNK) ? bytes - off : RT_COPY_CHUNK;
+      CU(cudaMemcpyAsync(ctx->hChunk[c & 1], (const unsigned char*)dsrc + off, n, cudaMemcpyDeviceToHost, ctx->stream));
+      CU(cudaEventRecord(ctx->evChunk[c & 1], ctx->stream));
+    }
+    if (c > 0) {
+      const size_t off = (c - 1) * (size_t)RT_COPY_CHUNK, n = (bytes - off < RT_COPY_CHUNK) ? bytes - off : RT_COPY_CHUNK;
+      CU(cudaEventSynchronize(ctx->evChunk[(c - 1) & 1]));
+      memcpy((unsigned char*)dst + off, ctx->hChunk[(c - 1) & 1], n);
+    }
+  }
   return RT_CUDA_OK;
 }
 
@@ -562,6 +553,66 @@ extern "C" int rt_cuda_readback_rgb8(rt_cuda_ctx* ctx, unsigned char* dst, float
   const size_t pixels = (size_t)ctx->localRows * ctx->W;
   if (!pixels) return RT_CUDA_OK;
   return copy_out(ctx, dst, ctx->dRgb8, pixels * 3);
+}
+
+/* Asynchronous readback: quantise on the render stream into one of two device buffers, copy on a
+ * second stream, return at once.  The next rt_cuda_render overlaps the copy. */
+extern "C" int rt_cuda_readback_rgb8_async(rt_cuda_ctx* ctx, unsigned char* dst, float maxColour, int* ticket) {
+  if (!ctx || !dst || !ticket) return RT_CUDA_ERR_INVALID_ARG;
+  if (!ctx->haveFrame) return RT_CUDA_ERR_NO_FRAME;
+  CU(cudaSetDevice(ctx->device));
+  const unsigned t = ctx->nextTicket & 1u;
+  rt_cuda_ctx::Ticket& k = ctx->tk[t];
+  if (k.pending) {            /* a third frame: finish the oldest first */
+    int rc = rt_cuda_readback_wait(ctx, (int)t);
+    if (rc) return rc;
+  }
+  const size_t pixels = (size_t)ctx->localRows * ctx->W;
+  const size_t bytes = pixels * 3;
+  *ticket = (int)t;
+  ctx->nextTicket++;
+  k.userDst = nullptr; k.bytes = 0;
+  if (!pixels) { k.pending = false; return RT_CUDA_OK; }
+  int rc = ensure_dev(ctx, k.dRgb, k.cap, ((pixels + 3) / 4) * 12);
+  if (rc) return rc;
+  unsigned char* target = dst;
+  if (!is_pinned(dst)) {      /* pageable destination: stage in pinned memory, copied out by the wait */
+    if (bytes > k.stageCap) {
+      if (k.hStage) cudaFreeHost(k.hStage);
+      k.hStage = nullptr; k.stageCap = 0;
+      CU(cudaMallocHost(&k.hStage, bytes));
+      k.stageCap = bytes;
+    }
+    target = k.hStage;
+    k.userDst = dst; k.bytes = bytes;
+  }
+  rc = quantise_into(ctx, k.dRgb, maxColour, ctx->stream);
+  if (rc) return rc;
+  CU(cudaEventRecord(k.evQuant, ctx->stream));
+  CU(cudaStreamWaitEvent(ctx->copyStream, k.evQuant, 0));
+  CU(cudaMemcpyAsync(target, k.dRgb, bytes, cudaMemcpyDeviceToHost, ctx->copyStream));
+  CU(cudaEventRecord(k.evCopy, ctx->copyStream));
+  k.pending = true;
+  return RT_CUDA_OK;
+}
+
+extern "C" int rt_cuda_readback_wait(rt_cuda_ctx* ctx, int ticket) {
+  if (!ctx || ticket < 0 || ticket > 1) return RT_CUDA_ERR_INVALID_ARG;
+  rt_cuda_ctx::Ticket& k = ctx->tk[ticket];
+  if (!k.pending) return RT_CUDA_OK;
+  CU(cudaSetDevice(ctx->device));
+  CU(cudaEventSynchronize(k.evCopy));
+  if (k.userDst) memcpy(k.userDst, k.hStage, k.bytes);
+  k.pending = false; k.userDst = nullptr;
+  return RT_CUDA_OK;
+}
+
+extern "C" int rt_cuda_flush_l2(rt_cuda_ctx* ctx) {
+  if (!ctx) return RT_CUDA_ERR_INVALID_ARG;
+  CU(cudaSetDevice(ctx->device));
+  if (!ctx->dFlush) CU(cudaMalloc(&ctx->dFlush, RT_FLUSH_BYTES));
+  CU(cudaMemsetAsync(ctx->dFlush, (int)(ctx->launches & 0xFF), RT_FLUSH_BYTES, ctx->stream));
+  return RT_CUDA_OK;
 }
 
 extern "C" int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out) {

@@ -170,7 +170,8 @@ static inline void build_clusters(const rt_sphere* spheres, uint32_t n, const fl
 }
 
 static inline void build_scene_soa(const rt_sphere* spheres, uint32_t n, const rt_light* lights,
-                                   uint32_t nl, std::vector<float4_>& h, SceneLayout& L) {
+                                   uint32_t nl, std::vector<float4_>& h, SceneLayout& L,
+                                   bool withClusters = true) {
   L = scene_layout(n, nl);
   h.assign(L.total, float4_{0.f, 0.f, 0.f, 0.f});
   float4_* filt = h.data() + L.offFilt;
@@ -200,8 +201,9 @@ static inline void build_scene_soa(const rt_sphere* spheres, uint32_t n, const r
     lpos[l] = float4_{lights[l].pos.x, lights[l].pos.y, lights[l].pos.z, 0.f};
     lcol[l] = float4_{lights[l].col.x, lights[l].col.y, lights[l].col.z, 0.f};
   }
-  build_clusters(spheres, n, filt, h.data() + L.offCfilt, h.data() + L.offMfilt,
-                 reinterpret_cast<unsigned short*>(h.data() + L.offMidx), L.nc, L.ncPad);
+  if (withClusters)
+    build_clusters(spheres, n, filt, h.data() + L.offCfilt, h.data() + L.offMfilt,
+                   reinterpret_cast<unsigned short*>(h.data() + L.offMidx), L.nc, L.ncPad);
 }
 
 }  // namespace rtg

@@ -7,8 +7,16 @@
  * the command line and does not wait for a key press (main.cpp:505).
  *
  *   rt_gamma [--width W] [--height H] [--alias A] [--zoom Z] [--depth S]
- *            [--spheres N] [--lights L] [--seed K] [--device D] [--list]
- *            [--out file.ppm|file.png] [--frames F] [--scene file] [--save-scene file] [--accel]
+ *            [--spheres N] [--lights L] [--seed K] [--device D] [--gpus G] [--list]
+ *            [--out file.ppm|file.png] [--frames F] [--zoom-step dZ] [--scene file] [--save-scene file] [--accel]
+ *
+ * --gpus G     the frame is sharded by row strips over G GPUs of this box (include/rt_cuda_multi.h:
+ *              one stream per device, NCCL max all-reduce + RGB8 all-gather); same bytes as 1 GPU.
+ * --frames F   an animation with the scene resident on the device: frame f is rendered with
+ *              zoom + f*dZ (--zoom-step).  The quantised frame f is copied back asynchronously
+ *              (rt_cuda_readback_rgb8_async, pinned double buffer) and written to disk while the
+ *              GPU renders frame f+1.  With F > 1 and a `%` in --out (e.g. frame_%03d.ppm) every
+ *              frame is written, otherwise only the last.
  */
 #include <chrono>
 #include <cstdio>
@@ -19,6 +27,7 @@
 #include <vector>
 
 #include "rt_cuda.h"
+#include "rt_cuda_multi.h"
 #include "rt_scene.h"
 #include "rt_png.h"
 
@@ -45,7 +54,8 @@ int main(int argc, char** argv) {
   int depth = 6;                             /* raytraceStack.h:10 */
   unsigned nSpheres = 0, nLights = 4, frames = 1;
   unsigned long long seed = 0;
-  int device = 0, accel = 0;                 /* --accel: optional two-level cluster filter (same frame, faster from ~768 spheres) */
+  int device = 0, accel = 0, gpus = 0;
+  float zoomStep = 0.f;                 /* --accel: optional two-level cluster filter (same frame, faster from ~768 spheres) */
   std::string out = "testPPM.ppm";           /* main.cpp:501 */
   std::string sceneFile, saveScene;
 
@@ -64,6 +74,8 @@ int main(int argc, char** argv) {
     else if (!strcmp(argv[i], "--seed")) seed = strtoull(need("--seed"), nullptr, 0);
     else if (!strcmp(argv[i], "--device")) device = atoi(need("--device"));
     else if (!strcmp(argv[i], "--frames")) frames = (unsigned)atoi(need("--frames"));
+    else if (!strcmp(argv[i], "--zoom-step")) zoomStep = (float)atof(need("--zoom-step"));
+    else if (!strcmp(argv[i], "--gpus")) gpus = atoi(need("--gpus"));
     else if (!strcmp(argv[i], "--out")) out = need("--out");
     else if (!strcmp(argv[i], "--scene")) sceneFile = need("--scene");
     else if (!strcmp(argv[i], "--save-scene")) saveScene = need("--save-scene");
@@ -78,8 +90,8 @@ int main(int argc, char** argv) {
       return 0;
     } else {
       fprintf(stderr, "usage: %s [--width W] [--height H] [--alias A] [--zoom Z] [--depth S] "
-                      "[--spheres N] [--lights L] [--seed K] [--device D] [--frames F] [--out file.ppm] [--scene file] "
-                      "[--save-scene file] [--accel] [--list]\n",
+                      "[--spheres N] [--lights L] [--seed K] [--device D] [--gpus G] [--frames F] [--zoom-step dZ] "
+                      "[--out file.ppm|file.png] [--scene file] [--save-scene file] [--accel] [--list]\n",
               argv[0]);
       return EXIT_FAILURE;
     }
@@ -115,6 +127,65 @@ int main(int argc, char** argv) {
     return EXIT_FAILURE;
   }
 
+  const bool png = out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0;      /* --out x.png: PNG instead of PPM */
+  const bool perFrame = frames > 1 && out.find('%') != std::string::npos;
+  auto write_frame = [&](const unsigned char* rgb, unsigned f) -> bool {
+    char name[1024];
+    if (perFrame) snprintf(name, sizeof name, out.c_str(), f); else snprintf(name, sizeof name, "%s", out.c_str());
+    const bool ok = png ? rtpng::write_rgb8(name, rgb, width, height) : save_ppm(rgb, name, width, height);
+    if (ok) printf("wrote %s\n", name);
+    return ok;
+  };
+  const size_t frameBytes = (size_t)width * height * 3;
+  if (frames == 0) frames = 1;
+
+  if (gpus > 0) {
+    /* ---- the frame sharded over `gpus` devices of this box ---- */
+    rt_cuda_multi* m = nullptr;
+    if (rt_cuda_multi_init(gpus, nullptr, &m) != RT_CUDA_OK) {
+      fprintf(stderr, "! Opening %d CUDA devices failed (%d present)\n", gpus, rt_cuda_device_count());
+      return EXIT_FAILURE;
+    }
+    auto mcheck = [&](int status, const char* what) {
+      if (status != RT_CUDA_OK) {
+        fprintf(stderr, "! %s: %s %s\n", what, rt_cuda_strerror(status), rt_cuda_multi_last_error(m));
+        exit(EXIT_FAILURE);
+      }
+    };
+    if (accel) mcheck(rt_cuda_multi_set_option(m, "accel", 1), "Selecting the accelerated mode");
+    char info[512];
+    for (int g = 0; g < gpus; ++g)
+      if (rt_cuda_device_info(g, info, sizeof info) == RT_CUDA_OK) printf("%s\n", info);
+    mcheck(rt_cuda_multi_upload_scene(m, spheres.data(), (unsigned)spheres.size(), lights.data(), (unsigned)lights.size()),
+           "Copying the scene to the devices");
+    std::vector<unsigned char> rgb(frameBytes);
+    float maxColourValue = 1.f;
+    for (unsigned f = 0; f < frames; ++f) {
+      auto t0 = std::chrono::steady_clock::now();
+      mcheck(rt_cuda_multi_render(m, width, height, zoom + (float)f * zoomStep, alias, depth, 0), "Enqueueing the frame");
+      mcheck(rt_cuda_multi_synchronize(m), "Waiting for commands to finish");
+      auto t1 = std::chrono::steady_clock::now();
+      printf("Exec time: %.5f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count());
+      mcheck(rt_cuda_multi_readback_rgb8(m, 0, rgb.data(), &maxColourValue), "Reading the image back");
+      if ((perFrame || f + 1 == frames) && !write_frame(rgb.data(), f)) return EXIT_FAILURE;
+    }
+    unsigned long long rays = 0;
+    float stepMs = 0.f;
+    for (int g = 0; g < gpus; ++g) {
+      rt_cuda_stats st;
+      if (rt_cuda_get_stats(rt_cuda_multi_context(m, g), &st) == RT_CUDA_OK) {
+        rays += st.rays;
+        printf("  gpu %d: rows %u  trace kernel %.3f ms  rays %llu\n", g, st.local_rows, st.kernel_ms, (unsigned long long)st.rays);
+      }
+      float ms = 0.f;
+      if (rt_cuda_multi_step_ms(m, g, &ms) == RT_CUDA_OK && ms > stepMs) stepMs = ms;
+    }
+    printf("%d GPUs: step %.3f ms (max over devices)  rays %llu (%.1f Mrays/s)  max colour %g\n", gpus, stepMs, rays,
+           stepMs > 0 ? rays / stepMs / 1e3 : 0.0, maxColourValue);
+    rt_cuda_multi_destroy(m);
+    return 0;
+  }
+
   rt_cuda_ctx* ctx = nullptr;
   check(rt_cuda_init(device, &ctx), "Opening the CUDA device");
   if (accel) check(rt_cuda_set_option(ctx, "accel", 1), "Selecting the accelerated mode");
@@ -123,29 +194,40 @@ int main(int argc, char** argv) {
   check(rt_cuda_upload_scene(ctx, spheres.data(), (unsigned)spheres.size(), lights.data(),
                              (unsigned)lights.size()), "Copying the scene to the device", ctx);
 
-  std::vector<unsigned char> rgb((size_t)width * height * 3);
-  float maxColourValue = 1.f;
-  for (unsigned f = 0; f < frames; ++f) {
-    /* same interval as main.cpp:353-369: launch -> finish */
-    auto t0 = std::chrono::steady_clock::now();
-    check(rt_cuda_render(ctx, width, height, zoom, alias, depth), "Enqueueing kernel", ctx);
-    check(rt_cuda_synchronize(ctx), "Waiting for commands to finish", ctx);
-    auto t1 = std::chrono::steady_clock::now();
-    printf("Exec time: %.5f ms\n", std::chrono::duration<double, std::milli>(t1 - t0).count());
-    /* quantise on the device with the frame's own maximum, copy 3 B/px back */
-    check(rt_cuda_readback_rgb8(ctx, rgb.data(), 0.f), "Reading the image back", ctx);
+  /* pinned double buffer: frame f is on its way to the host while frame f+1 renders */
+  unsigned char* host[2] = {(unsigned char*)rt_cuda_host_alloc(frameBytes), (unsigned char*)rt_cuda_host_alloc(frameBytes)};
+  if (!host[0] || !host[1]) { fprintf(stderr, "! cannot allocate pinned host memory\n"); return EXIT_FAILURE; }
+  int ticket[2] = {-1, -1};
+  bool failed = false;
+  auto t_begin = std::chrono::steady_clock::now();
+  for (unsigned f = 0; f <= frames && !failed; ++f) {
+    if (f < frames) {
+      /* same interval as main.cpp:353-369 for a single frame: launch -> finish */
+      auto t0 = std::chrono::steady_clock::now();
+      check(rt_cuda_render(ctx, width, height, zoom + (float)f * zoomStep, alias, depth), "Enqueueing kernel", ctx);
+      if (frames == 1) {
+        check(rt_cuda_synchronize(ctx), "Waiting for commands to finish", ctx);
+        printf("Exec time: %.5f ms\n", std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t0).count());
+      }
+      /* quantise on the device with the frame's own maximum, copy 3 B/px back without waiting */
+      check(rt_cuda_readback_rgb8_async(ctx, host[f & 1], 0.f, &ticket[f & 1]), "Reading the image back", ctx);
+    }
+    if (f > 0) {               /* frame f-1: wait for its copy, write it while the GPU works on frame f */
+      const unsigned g = f - 1;
+      check(rt_cuda_readback_wait(ctx, ticket[g & 1]), "Waiting for the image", ctx);
+      if ((perFrame || g + 1 == frames) && !write_frame(host[g & 1], g)) failed = true;
+    }
   }
+  const double total_ms = std::chrono::duration<double, std::milli>(std::chrono::steady_clock::now() - t_begin).count();
+  if (frames > 1) printf("%u frames in %.3f ms (%.2f frames/s, render + readback + file output overlapped)\n", frames, total_ms,
+                         frames * 1e3 / total_ms);
   rt_cuda_stats st;
   check(rt_cuda_get_stats(ctx, &st), "Reading statistics", ctx);
-  maxColourValue = st.max_colour == 0.f ? 1.f : st.max_colour;
+  const float maxColourValue = st.max_colour == 0.f ? 1.f : st.max_colour;
   printf("kernel %.3f ms  rays %llu (%.1f Mrays/s)  sphere tests %llu  max colour %g\n", st.kernel_ms,
          (unsigned long long)st.rays, st.kernel_ms > 0 ? st.rays / st.kernel_ms / 1e3 : 0.0,
          (unsigned long long)(st.rays * st.sph_num), maxColourValue);
+  rt_cuda_host_free(host[0]); rt_cuda_host_free(host[1]);
   rt_cuda_destroy(ctx);
-
-  const bool png = out.size() > 4 && out.compare(out.size() - 4, 4, ".png") == 0;      /* --out x.png: PNG instead of PPM */
-  if (!(png ? rtpng::write_rgb8(out.c_str(), rgb.data(), width, height) : save_ppm(rgb.data(), out.c_str(), width, height)))
-    return EXIT_FAILURE;
-  printf("wrote %s\n", out.c_str());
-  return 0;
+  return failed ? EXIT_FAILURE : 0;
 }

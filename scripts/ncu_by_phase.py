@@ -1,0 +1,167 @@
+"""Development aid: attribute an ncu source-page capture of trace_kernel to the PHASES of a pass.
+
+    ncu -i X.ncu-rep --page source --csv --print-source sass > X.sass.csv
+    python scripts/ncu_by_phase.py X.sass.csv [--cubin K.cubin | --flags "-DRT_..."] [--kernel REGEX]
+
+Every SASS instruction carries its inlining chain (nvdisasm -gi, needs -lineinfo).  The chain is
+walked from the kernel body inwards; the first frame that lies in a pass / advance / helper function
+names the phase, and inside pass_* the line decides between set-up, filter loop, gather and resolve.
+Out-of-line helpers (IEEE division / square root, the exact test) are reported under their own name.
+Prints, per phase: share of executed warp instructions, share of stall samples, lane efficiency
+(thread instructions / 32 x warp instructions)."""
+import argparse, bisect, collections, csv, re, subprocess, sys, tempfile
+from pathlib import Path
+
+ROOT = Path(__file__).resolve().parent.parent
+CSRC = ROOT / "raytracer-gamma_b200" / "csrc"
+ap = argparse.ArgumentParser()
+ap.add_argument("sass_csv")
+ap.add_argument("--cubin")
+ap.add_argument("--flags", default="")
+ap.add_argument("--kernel", default=None, help="regex on the mangled kernel name (default: taken from the capture)")
+ap.add_argument("--lines", type=int, default=0, help="also print the N hottest source lines")
+ap.add_argument("--root", default=None, help="source tree of the captured build (default: this checkout)")
+args = ap.parse_args()
+if args.root:
+    ROOT = Path(args.root).resolve()
+    CSRC = ROOT / "raytracer-gamma_b200" / "csrc"
+
+rows = list(csv.reader(open(args.sass_csv)))
+kname = rows[0][1]
+hdr, data = rows[1], rows[2:]
+ix = {n: i for i, n in enumerate(hdr)}
+
+cubin = args.cubin
+if not cubin:
+    tmp = Path(tempfile.mkdtemp())
+    cubin = str(tmp / "k.cubin")
+    subprocess.run(["nvcc", "-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "--fmad=false", "-std=c++17",
+                    *args.flags.split(), f"-I{ROOT/'include'}", f"-I{CSRC}", "-cubin", "-o", cubin, str(CSRC / "rt_shim.cu")],
+                   check=True, stderr=subprocess.DEVNULL)
+dis = subprocess.run(["nvdisasm", "-gi", cubin], capture_output=True, text=True).stdout
+
+# ---- which text section is the captured kernel?  match template arguments of the demangled name
+def demangle(m):
+    return subprocess.run(["cu++filt", m], capture_output=True, text=True).stdout.strip()
+sections = re.findall(r"^\.text\.(\S+):", dis, flags=re.M)
+want = re.sub(r"\s+", "", kname).replace("(bool)", "").replace("(int)", "")
+target = None
+for s in sections:
+    d = re.sub(r"\s+", "", demangle(s)).replace("(bool)", "").replace("(int)", "")
+    if args.kernel:
+        if re.search(args.kernel, s):
+            target = s; break
+    elif d == want:
+        target = s; break
+if target is None:
+    sys.exit(f"kernel {kname} not found in the cubin (sections: {[demangle(s) for s in sections if 'trace' in s]})")
+
+# ---- per instruction: inlining chain and enclosing sub-function label
+insts = []   # (frames innermost->outermost as (file, line), subfunc or None)
+active = False; frames = []; pending = []; sub = None
+for line in dis.split("\n"):
+    m = re.match(r"\s*\.text\.(\S+):", line)
+    if m:
+        active = (m.group(1) == target); sub = None; continue
+    if not active:
+        continue
+    m = re.match(r"\$" + re.escape(target) + r"\$(\S+):", line.strip())
+    if m:
+        sub = m.group(1); continue
+    m = re.search(r'//## File "([^"]+)", line (\d+)( inlined at)?', line)
+    if m:
+        pending.append((m.group(1).split("/")[-1], int(m.group(2))))
+        if not m.group(3):
+            frames = pending; pending = []
+        continue
+    if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", line):
+        insts.append((frames, sub))
+assert len(insts) == len(data), (len(insts), len(data), "the cubin is not the captured build")
+
+def funcs_of(path):
+    out = []
+    for i, l in enumerate(open(path).read().split("\n"), 1):
+        m = re.match(r"(?:RT_HD(?:_NI)?|__device__ __forceinline__|__device__ __noinline__|__global__)\s+.*?(\w+)\(", l) or \
+            re.match(r"(?:template.*>\s*)?__device__.*?\s(\w+)\(", l)
+        if m:
+            out.append((i, m.group(1)))
+    return out
+SRC = {f: open(CSRC / f).read().split("\n") for f in ("rt_core.cuh", "rt_kernels.cuh")}
+FN = {f: funcs_of(CSRC / f) for f in SRC}
+def fn_at(f, l):
+    if f not in FN:
+        return None
+    j = bisect.bisect_right([x[0] for x in FN[f]], l) - 1
+    return FN[f][j][1] if j >= 0 else None
+KERNEL_FUNCS = {"trace_body", "trace_kernel", "trace_kernel_const", "__launch_bounds__"}
+
+def sub_phase(f, l, fn):
+    """inside pass_*: set-up / loop / gather-call / resolve by looking backwards for the enclosing marker"""
+    src = SRC[f]
+    for k in range(l - 1, max(0, l - 200), -1):
+        t = src[k]
+        if re.search(r"for \(uint32_t base|for \(; base < nPad", t): return "filter loop"
+        if re.search(r"for \(int k = 0; k < maxc", t): return "resolve" if "maxc2" in t or "accel" not in fn else "members"
+        if re.search(r"const unsigned comb", t) and k < l - 1: return "loop exit / gather call"
+        if re.search(r"if \(overflow\)", t): return "epilogue"
+        if re.search(r"__device__ __forceinline__ void pass_", t): return "set-up"
+    return "set-up"
+
+def kernel_phase(l):
+    src = SRC["rt_kernels.cuh"]
+    for k in range(l - 1, max(0, l - 400), -1):
+        t = src[k]
+        if "---- per-warp reductions" in t: return "kernel: epilogue"
+        if "---- advance the served slots" in t: return "kernel: advance glue"
+        if "---- vote ----" in t: return "kernel: vote + dispatch"
+        if "---- refill ----" in t: return "kernel: refill"
+        if "trace_body(" in t or "trace_kernel(" in t: return "kernel: prologue"
+    return "kernel: other"
+
+def classify(frames, sub):
+    if sub:
+        d = demangle(sub)
+        return "out-of-line: " + re.sub(r"\(.*", "", d).replace("rtg::", "")
+    chain = list(reversed(frames))          # outermost first
+    for f, l in chain:
+        fn = fn_at(f, l)
+        if fn is None or fn in KERNEL_FUNCS:
+            continue
+        if fn.startswith("pass_"):
+            return f"{fn}: {sub_phase(f, l, fn)}"
+        if fn in ("gather", "gather1", "gather2", "member_bits"):
+            return "gather"
+        if fn in ("advance_slot", "advance", "after_matte", "after_contain", "unwind", "fresnel_term", "setup_shadow_batch"):
+            return "advance (state machine)"
+        if fn in ("start_task", "work_to_task", "set_trace_query"):
+            return "kernel: refill"
+        return "other: " + fn
+    f, l = chain[0] if chain else ("?", 0)
+    return kernel_phase(l) if f == "rt_kernels.cuh" else "kernel: other"
+
+inst = collections.Counter(); samp = collections.Counter(); thr = collections.Counter(); byline = collections.Counter(); static = collections.Counter()
+ti = ts = 0
+for r, (frames, sub) in zip(data, insts):
+    a = int(r[ix["Instructions Executed"]]); b = int(r[ix["# Samples"]]); t = int(r[ix["Thread Instructions Executed"]])
+    key = classify(frames, sub)
+    inst[key] += a; samp[key] += b; thr[key] += t; ti += a; ts += b; static[key] += 1
+    if frames:
+        byline[frames[-1] if frames[-1][0] == "rt_kernels.cuh" else frames[0]] += b
+print(f"kernel {kname}")
+print(f"warp instructions {ti}  stall samples {ts}")
+print(f"{'phase':44s} {'inst %':>8s} {'samples %':>10s} {'lane eff':>9s} {'SASS':>6s}")
+for k, c in sorted(samp.items(), key=lambda kv: -kv[1]):
+    if inst[k] == 0 and c == 0:
+        continue
+    print(f"{k:44s} {100 * inst[k] / ti:8.2f} {100 * c / ts:10.2f} {thr[k] / max(1, 32 * inst[k]):9.3f} {static[k]:6d}")
+print(f"static SASS instructions {len(data)} ({len(data) * 16 / 1024:.1f} KB)")
+grp = collections.Counter(); grs = collections.Counter()
+for k in inst:
+    g = "filter loops" if k.endswith("filter loop") else "everything else"
+    grp[g] += inst[k]; grs[g] += samp[k]
+for g in grp:
+    print(f"== {g:40s} {100 * grp[g] / ti:8.2f} {100 * grs[g] / ts:10.2f}")
+if args.lines:
+    print("hottest lines (stall samples, outermost frame in rt_kernels.cuh)")
+    for (f, l), c in byline.most_common(args.lines):
+        print(f"{100 * c / ts:6.2f}%  {f}:{l}  {SRC.get(f, [''] * (l + 1))[l - 1].strip()[:90]}")

@@ -17,7 +17,6 @@ cases = [
     ("accel synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"accel": 2}),
     ("accel synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"accel": 1}),
     ("accel synth4096 2K a1 s8", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {"accel": 1}),
-    ("wavefront s1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"engine": 2}),
 ]
 if len(sys.argv) > 1:
     cases = [c for c in cases if any(a in c[0] for a in sys.argv[1:])]

@@ -6,7 +6,7 @@ import __graft_entry__ as graft
 pkg = graft.load_package()
 with pkg.Renderer(0) as r:
     for n, W, H, alias, S, opts in [(0, 96, 64, 2.0, 6, {}), (40, 80, 48, 1.0, 8, {}), (300, 64, 40, 2.0, 8, {}),
-                                    (300, 64, 40, 1.0, 8, {"accel": 2}), (300, 48, 32, 1.0, 6, {"engine": 2, "pool": 500}),
+                                    (300, 64, 40, 1.0, 8, {"accel": 2}), (300, 48, 32, 1.0, 6, {"staging": 1}),
                                     (300, 48, 32, 1.0, 6, {"no_filter": 1}), (1100, 48, 32, 1.0, 8, {"accel": 1})]:
         sph, lgt = pkg.default_scene() if n == 0 else pkg.synth_scene(n, 4)
         for k, v in opts.items():

@@ -1,38 +1,70 @@
 """BASELINE config 5: sphere-count sweep 16..4096 at 3840x2160, 1 spp, depth 8 — shared-memory (TMA bulk)
-vs __constant__ staging.  Prints one JSON line per (N, staging)."""
-import json, sys
+vs constant-bank staging, at 1 GPU or (--gpus N) through the native multi-GPU path (one process,
+rt_cuda_multi_init).  Prints one JSON line per (N, staging); with --gpus N > 1 the time is the whole step
+(strips + NCCL all-reduce + quantise + NCCL all-gather + assembly, max over devices) and `identical`
+says the assembled frame equals the 1-GPU frame byte for byte."""
+import argparse, json, sys
 from pathlib import Path
 sys.path.insert(0, str(Path(__file__).resolve().parent.parent))
+import numpy as np
 import __graft_entry__ as graft
 
+ap = argparse.ArgumentParser()
+ap.add_argument("--gpus", type=int, default=1)
+ap.add_argument("--counts", default="16,32,64,128,256,512,1024,2048,4096")
+ap.add_argument("--reps", type=int, default=3)
+args = ap.parse_args()
 pkg = graft.load_package()
 W, H, alias, S = 3840, 2160, 1.0, 8
-r = pkg.Renderer(0)
+G = args.gpus
+one = pkg.Renderer(0)
 peak = 148 * 128 * 2 * 1.965e9 / 1e12
-print(json.dumps({"device": pkg.device_info(0), "ffma_peak_tflops": round(r.ffma_peak(8192), 2), "nominal_peak_tflops": round(peak, 2),
-                  "workload": f"synth(N, 4 lights) {W}x{H} alias {alias:g} stack {S}"}))
-for n in (16, 32, 64, 128, 256, 512, 1024, 2048, 4096):
+print(json.dumps({"device": pkg.device_info(0), "gpus": G, "ffma_peak_tflops": round(one.ffma_peak(8192), 2),
+                  "nominal_peak_tflops_per_gpu": round(peak, 2), "workload": f"synth(N, 4 lights) {W}x{H} alias {alias:g} stack {S}"}))
+multi = pkg.MultiRenderer(gpus=G) if G > 1 else None
+NAMES = {1: "constant bank (launch parameter)", 2: "shared (TMA bulk)",
+         3: "shared (TMA bulk) + accel (cluster filter; not brute force, frac is the contract's flops over time)"}
+for n in [int(x) for x in args.counts.split(",")]:
     sph, lgt = pkg.synth_scene(n, 4)
-    r.upload_scene(sph, lgt)
+    one.upload_scene(sph, lgt)
+    single = None
+    if multi:
+        multi.upload_scene(sph, lgt)
+        one.render(W, H, -4.0, alias, S)
+        single = one.readback_rgb8(0.0)
     for staging in (1, 2, 3):                 # 3 = shared staging + the optional accelerated mode
         if staging == 1 and n > 1024:
             continue
         if staging == 3 and n < 64:
             continue
+        r = multi or one
         r.set_option("staging", 2 if staging == 3 else staging)
         r.set_option("accel", 2 if staging == 3 else 0)
         best = None
-        for _ in range(3):
-            r.render(W, H, -4.0, alias, S)
-            st = r.stats()
-            if best is None or st["kernel_ms"] < best["kernel_ms"]:
-                best = st
+        for _ in range(args.reps):
+            if multi:
+                multi.render(W, H, -4.0, alias, S, 4)
+                multi.synchronize()
+                ms = max(multi.step_ms(g) for g in range(G))
+                sts = [multi.stats(g) for g in range(G)]
+                st = {k: sum(s[k] for s in sts) for k in ("rays", "null_rays", "contain_tests", "active_lane_iters", "lane_iters")}
+                st["kernel_ms_max"] = max(s["kernel_ms"] for s in sts)
+            else:
+                one.render(W, H, -4.0, alias, S)
+                st = one.stats()
+                ms = st["kernel_ms"]
+            if best is None or ms < best[0]:
+                best = (ms, st)
         r.set_option("staging", 0)
         r.set_option("accel", 0)
-        ms = best["kernel_ms"]
-        tests = (best["rays"] - best["null_rays"]) * n
-        flops = 17.0 * tests + 8.0 * best["contain_tests"]
-        print(json.dumps({"spheres": n, "staging": {1: "__constant__", 2: "shared (TMA bulk)", 3: "shared (TMA bulk) + accel (cluster filter; not brute force, frac is the contract's flops over time)"}[staging], "kernel_ms": round(ms, 3),
-                          "frames_per_s": round(1e3 / ms, 2), "Mrays_per_s": round(best["rays"] / ms / 1e3, 1),
-                          "tflops_17": round(flops / ms / 1e9, 2), "frac_of_nominal_peak": round(flops / ms / 1e9 / peak, 3),
-                          "rays": best["rays"], "lane_utilisation": round(best["active_lane_iters"] / max(1, best["lane_iters"]), 3)}))
+        ms, st = best
+        tests = (st["rays"] - st["null_rays"]) * n
+        flops = 17.0 * tests + 8.0 * st["contain_tests"]
+        line = {"spheres": n, "gpus": G, "staging": NAMES[staging], ("step_ms" if multi else "kernel_ms"): round(ms, 3),
+                "frames_per_s": round(1e3 / ms, 2), "Mrays_per_s": round(st["rays"] / ms / 1e3, 1),
+                "tflops_17": round(flops / ms / 1e9, 2), "frac_of_nominal_peak": round(flops / ms / 1e9 / (peak * G), 3),
+                "rays": st["rays"], "lane_utilisation": round(st["active_lane_iters"] / max(1, st["lane_iters"]), 3)}
+        if multi:
+            line["trace_kernel_ms_max"] = round(st["kernel_ms_max"], 3)
+            line["identical"] = bool(np.array_equal(multi.readback_rgb8(0)[0], single))
+        print(json.dumps(line), flush=True)

@@ -18,14 +18,49 @@ def _declared(header: str):
 
 
 def test_library_exports_every_declared_symbol(pkg):
-    lib = ctypes.CDLL(str(pkg.LIB_PATH))
-    names = _declared("rt_cuda.h") + _declared("rt_scene.h")
-    assert len(names) >= 22
-    for n in names:
-        assert hasattr(lib, n), f"{n} declared in include/ but not exported"
-    # and the binding covers them all
-    bound = {n for n, _, _ in pkg.C_ABI}
-    assert set(names) <= bound, set(names) - bound
+    """One library per header: rt_cuda.h -> librt_cuda.so, rt_cuda_multi.h -> librt_cuda_multi.so (NCCL),
+    rt_scene.h -> librt_scene.so (host only: the reference arm of bench.py maps no CUDA library)."""
+    total = 0
+    for header, path, table in (("rt_cuda.h", pkg.LIB_PATH, pkg.C_ABI), ("rt_scene.h", pkg.SCENE_LIB_PATH, pkg.SCENE_ABI),
+                                ("rt_cuda_multi.h", pkg.MULTI_LIB_PATH, pkg.MULTI_ABI)):
+        pkg.load()                                  # librt_cuda_multi.so resolves librt_cuda.so through its RPATH
+        lib = ctypes.CDLL(str(path))
+        names = _declared(header)
+        if header == "rt_cuda.h":
+            names = [n for n in names if not n.startswith("rt_cuda_multi_")]
+        total += len(names)
+        for n in names:
+            assert hasattr(lib, n), f"{n} declared in include/{header} but not exported by {path.name}"
+        bound = {n for n, _, _ in table}            # and the binding covers them all
+        assert set(names) <= bound, set(names) - bound
+    assert total >= 50
+    out = subprocess.run(["nm", "-D", "--defined-only", str(pkg.SCENE_LIB_PATH)], capture_output=True, text=True).stdout
+    assert "cuda" not in out.lower()
+    needed = subprocess.run(["readelf", "-d", str(pkg.SCENE_LIB_PATH)], capture_output=True, text=True).stdout
+    assert "cuda" not in needed.lower() and "nccl" not in needed.lower()
+
+
+def test_multi_layout_matches_the_python_statement(pkg):
+    """rt_cuda_multi_shard_rows / _shard_pitch / _locate_row (C) against parallel.py and numpy."""
+    import importlib
+    par = importlib.import_module(pkg.__name__ + ".parallel")
+    for H, W, strip, G in [(45, 70, 4, 2), (101, 33, 16, 8), (7, 5, 3, 4), (64, 64, 16, 4), (4320, 7680, 4, 8), (1, 9, 4, 3)]:
+        lay = pkg.multi_layout(W, H, strip, G)
+        ref = par.shard_layout(H, W, strip, G)
+        assert lay["rows"] == ref["rows"] and lay["pitch"] == ref["pitch"], (H, W, strip, G)
+        for row in range(0, H, max(1, H // 23)):
+            assert pkg.multi_locate_row(row, strip, G) == par.local_row_of(row, strip, G)
+
+
+def test_multi_library_refuses_without_a_gpu(pkg):
+    if pkg.device_count() > 0:
+        pytest.skip("a GPU is present")
+    with pytest.raises(pkg.RtCudaError) as e:
+        pkg.MultiRenderer(gpus=2)
+    assert e.value.status == -2
+    lib = pkg._multi_lib()
+    assert lib.rt_cuda_multi_render(None, 8, 8, -4.0, 1.0, 6, 0) == -1
+    assert pkg.load().rt_cuda_strerror(-8) == b"RT_CUDA_ERR_NCCL"
 
 
 def test_signatures_are_plain_c(pkg):

@@ -119,9 +119,8 @@ def test_staging_and_filter_variants_agree(pkg, orc_mod, gpu):
     invisible in the output."""
     sph, lgt = pkg.synth_scene(200, 4, seed=3)
     base, _, st0 = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8)
-    for opts in ({"staging": 1}, {"staging": 2}, {"no_filter": 1}, {"blocks_per_sm": 1}, {"slots": 2}, {"slots": 3},
-                 {"min_blocks": 3}, {"min_blocks": 4}, {"prefetch": 1}, {"engine": 1}, {"engine": 2},
-                 {"engine": 2, "pool": 777}, {"engine": 2, "no_filter": 1}, {"accel": 2}, {"accel": 2, "no_filter": 1}):
+    for opts in ({"staging": 1}, {"staging": 2}, {"no_filter": 1}, {"blocks_per_sm": 1}, {"staging": 1, "no_filter": 1},
+                 {"accel": 2}, {"accel": 2, "no_filter": 1}):
         fb, _, st = _render(gpu, sph, lgt, 160, 90, -4.0, 1.0, 8, **opts)
         assert np.array_equal(orc_mod.canon(fb), orc_mod.canon(base)), opts
         assert st["rays"] == st0["rays"]
@@ -182,25 +181,192 @@ def test_accelerated_mode_matches_oracle(pkg, orc_mod, oracle, gpu):
     assert _render(gpu, sph, lgt, 64, 48, -4.0, 1.0, 6, accel=1)[2]["accel"] == 1
 
 
-@pytest.mark.parametrize("engine", [1, 2])
-def test_both_engines_match_oracle(pkg, orc_mod, oracle, gpu, engine):
-    """The persistent kernel and the wavefront engine are two schedules of the same per-sample
-    arithmetic: each is bit-exact against the oracle, single- and multi-sample, whole frame and strips."""
+def test_strips_and_multisample_match_oracle(pkg, orc_mod, oracle, gpu):
+    """Single- and multi-sample frames, whole frame and strips, against the oracle with its work counters."""
     for (sph, lgt), (W, H, alias, S) in [(pkg.default_scene(), (200, 150, 3.0, 6)),
                                           (pkg.synth_scene(300, 4, seed=4), (160, 90, 2.0, 8)),
                                           (pkg.synth_scene(64, 2, seed=8), (97, 61, 1.0, 5))]:
-        fb, mx, st = _render(gpu, sph, lgt, W, H, -4.0, alias, S, engine=engine, pool=5000)
-        assert st["engine"] == engine
+        fb, mx, st = _render(gpu, sph, lgt, W, H, -4.0, alias, S)
+        assert st["engine"] == 1
         ref, ctr = oracle.render(sph, lgt, W, H, -4.0, alias, S)
         _assert_parity(orc_mod, oracle, ref, fb)
         for k in ("rays", "shadow_rays", "contain_queries", "contain_tests", "samples"):
             assert st[k] == ctr[k], k
         assert mx == oracle.max_colour(ref)
-        gpu.set_option("engine", engine)
         gpu.render_strips(W, H, -4.0, alias, S, 8, 1, 3)
         part, _ = gpu.readback()
-        gpu.set_option("engine", 0)
         assert np.array_equal(orc_mod.canon(part), orc_mod.canon(fb[pkg.local_rows(H, 8, 1, 3)]))
+
+
+def test_two_contexts_interleaved(pkg, orc_mod, oracle):
+    """Two live contexts on device 0 holding different small scenes, rendered in turn with every staging:
+    each frame is its own scene's (the filter records of the constant-bank path travel with the launch,
+    no module-global state is shared between contexts)."""
+    a, b = pkg.Renderer(0), pkg.Renderer(0)
+    try:
+        sa, la = pkg.default_scene()
+        sb, lb = pkg.synth_scene(40, 4, seed=2)
+        ref_a, _ = oracle.render(sa, la, 160, 120, -4.0, 2.0, 6)
+        ref_b, _ = oracle.render(sb, lb, 160, 120, -4.0, 1.0, 8)
+        a.upload_scene(sa, la)
+        b.upload_scene(sb, lb)            # uploaded AFTER a's scene, before a renders
+        for staging in (0, 1, 2):
+            a.set_option("staging", staging)
+            b.set_option("staging", staging)
+            for _ in range(2):
+                a.render(160, 120, -4.0, 2.0, 6)
+                b.render(160, 120, -4.0, 1.0, 8)       # both in flight on their own streams
+                fa, _ = a.readback()
+                fb, _ = b.readback()
+                _assert_parity(orc_mod, oracle, ref_a, fa)
+                _assert_parity(orc_mod, oracle, ref_b, fb)
+            if staging:
+                assert a.stats()["staging"] == staging and b.stats()["staging"] == staging
+    finally:
+        a.close()
+        b.close()
+
+
+def test_failed_render_leaves_no_frame(pkg, gpu):
+    """A render that fails validation must not publish a frame: later readbacks say NO_FRAME
+    or keep serving the previous, complete frame — never uninitialised pixels at the new size."""
+    lib = pkg.load()
+    sph, lgt = pkg.default_scene()
+    fresh = pkg.Renderer(0)
+    try:
+        fresh.upload_scene(sph, lgt)
+        assert lib.rt_cuda_render(fresh._ctx, 16, 16, -4.0, 65536.0, 6) == -6        # alias^2 samples do not fit 32 bits
+        assert lib.rt_cuda_render(fresh._ctx, 16, 16, -4.0, 2.0e6, 6) == -6          # beyond the iteration cap
+        out = np.zeros((16, 16, 3), np.float32)
+        assert lib.rt_cuda_readback(fresh._ctx, out.ctypes.data, None) == -5          # nothing was published
+        fresh.render(16, 16, -4.0, 1.0, 6)
+        good, _ = fresh.readback()
+        assert lib.rt_cuda_render(fresh._ctx, 16, 16, -4.0, 65536.0, 6) == -6
+        again, _ = fresh.readback()                                                  # the previous frame is intact
+        assert fresh.width == 16 and np.array_equal(good.view(np.uint32), again.view(np.uint32))
+    finally:
+        fresh.close()
+
+
+def test_async_readback_overlaps_and_matches(pkg, orc_mod, oracle, gpu):
+    """rt_cuda_readback_rgb8_async: a multi-frame loop with the scene resident (zoom animated), two
+    readbacks in flight, pinned and pageable destinations: every frame equals the oracle's frame."""
+    sph, lgt = pkg.synth_scene(48, 3, seed=6)
+    W, H, S = 128, 96, 6
+    zooms = [-4.0, -4.5, -5.0, -5.5, -6.0]
+    gpu.upload_scene(sph, lgt)
+    pinned = [pkg.HostBuffer(W * H * 3), pkg.HostBuffer(W * H * 3)]
+    pageable = [np.empty(W * H * 3, np.uint8), np.empty(W * H * 3, np.uint8)]
+    for bufs in (pinned, pageable):
+        tickets, got = [None, None], []
+        for f, z in enumerate(zooms + [None]):
+            if z is not None:
+                gpu.render(W, H, z, 1.0, S)
+                tickets[f & 1] = gpu.readback_rgb8_async(bufs[f & 1])
+            if f > 0:
+                gpu.readback_wait(tickets[(f - 1) & 1])
+                b = bufs[(f - 1) & 1]
+                got.append(np.array(b.array if isinstance(b, pkg.HostBuffer) else b).reshape(H, W, 3).copy())
+        for z, frame in zip(zooms, got):
+            ref, _ = oracle.render(sph, lgt, W, H, z, 1.0, S)
+            assert np.array_equal(frame, oracle.quantise(ref, oracle.max_colour(ref))), z
+    for h in pinned:
+        h.free()
+    # the synchronous readback takes the chunked pinned path for large pageable buffers: same bytes
+    sph, lgt = pkg.synth_scene(64, 4, seed=1)
+    gpu.upload_scene(sph, lgt)
+    gpu.render(2600, 1500, -4.0, 1.0, 4)            # 11.7 MB of RGB8: more than one 8 MiB chunk
+    a = gpu.readback_rgb8()
+    hb = pkg.HostBuffer(2600 * 1500 * 3)
+    t = gpu.readback_rgb8_async(hb)
+    gpu.readback_wait(t)
+    assert np.array_equal(a.reshape(-1), hb.array)
+    hb.free()
+
+
+def _needs_gpus(pkg, n):
+    if pkg.device_count() < n:
+        pytest.skip(f"needs {n} GPUs on this box")
+
+
+@pytest.mark.parametrize("gpus", [1, 2, 4, 8])
+def test_multi_gpu_c_abi_matches_oracle(pkg, orc_mod, oracle, gpus):
+    """include/rt_cuda_multi.h, one process driving `gpus` devices (ncclCommInitAll): strips + NCCL max
+    all-reduce + quantise + NCCL all-gather + assembly give the oracle's quantised frame byte for byte,
+    with the global maximum; ragged frames (rows not divisible by strips x ranks) included."""
+    _needs_gpus(pkg, gpus)
+    with pkg.MultiRenderer(gpus=gpus) as m:
+        assert m.world == gpus and m.local == gpus
+        for (sph, lgt), (W, H, alias, S, strip) in [(pkg.default_scene(), (200, 150, 3.0, 6, 0)),
+                                                    (pkg.synth_scene(300, 4, seed=4), (161, 91, 2.0, 8, 4)),
+                                                    (pkg.synth_scene(64, 2, seed=8), (97, 7, 1.0, 5, 16))]:
+            m.upload_scene(sph, lgt)
+            for accel in (0, 2):
+                m.set_option("accel", accel)
+                m.render(W, H, -4.0, alias, S, strip)
+                ref, ctr = oracle.render(sph, lgt, W, H, -4.0, alias, S)
+                want = oracle.quantise(ref, oracle.max_colour(ref))
+                for local in range(m.local):
+                    frame, mx = m.readback_rgb8(local)
+                    assert mx == oracle.max_colour(ref)
+                    assert np.array_equal(frame, want), (gpus, local, W, H)
+                assert sum(m.stats(g)["rays"] for g in range(m.local)) == ctr["rays"]
+                assert m.step_ms(0) > 0
+            m.set_option("accel", 0)
+
+
+@pytest.mark.parametrize("gpus", [1, 2, 8])
+def test_host_program_multi_gpu(pkg, tmp_path, gpus):
+    """`rt_gamma --gpus N` (the C++ host over rt_cuda_multi.h, no Python in the data path) writes the
+    reference CPU render's PPM."""
+    import subprocess
+    _needs_gpus(pkg, gpus)
+    out = tmp_path / "multi.ppm"
+    res = subprocess.run([str(pkg.HOST_BIN), "--gpus", str(gpus), "--out", str(out)], capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert hashlib.md5(out.read_bytes()).hexdigest() == FACTS["default_800x600_a3_s6"]["ppm_md5"]
+    assert f"{gpus} GPUs: step" in res.stdout
+
+
+def test_multi_gpu_one_process_per_gpu_nccl(pkg, tmp_path):
+    """The torchrun flavour (rt_cuda_multi_init_rank, NCCL inside the library, one process per GPU) on 2
+    GPUs: the assembled frame on every rank equals the oracle's quantised frame."""
+    import os
+    import subprocess
+    import sys
+    import textwrap
+    _needs_gpus(pkg, 2)
+    worker = tmp_path / "w.py"
+    worker.write_text(textwrap.dedent("""
+        import os, sys
+        import numpy as np, torch, torch.distributed as dist
+        sys.path.insert(0, %r)
+        import __graft_entry__ as graft
+        pkg = graft.load_package(); om = graft.load_oracle()
+        rank, world, lr = int(os.environ["RANK"]), int(os.environ["WORLD_SIZE"]), int(os.environ["LOCAL_RANK"])
+        torch.cuda.set_device(lr)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
+        box = [pkg.multi_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0)
+        m = pkg.MultiRenderer(rank=rank, world=world, uid=box[0], device=lr)
+        sph, lgt = pkg.synth_scene(200, 4, seed=3)
+        W, H, alias, S = 173, 99, 2.0, 7
+        m.upload_scene(sph, lgt)
+        m.render(W, H, -4.0, alias, S, 4)
+        frame, mx = m.readback_rgb8(0)
+        oracle = om.Oracle("port")
+        ref, _ = oracle.render(sph, lgt, W, H, -4.0, alias, S)
+        assert mx == oracle.max_colour(ref), (mx, oracle.max_colour(ref))
+        assert np.array_equal(frame, oracle.quantise(ref, mx))
+        print("RANK_OK", rank)
+        m.close(); dist.barrier(); dist.destroy_process_group()
+    """) % str(pkg.REPO_ROOT))
+    env = dict(os.environ, MASTER_ADDR="127.0.0.1")
+    res = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", "2",
+                          "--master-addr", "127.0.0.1", "--master-port", "29547", str(worker)],
+                         capture_output=True, text=True, env=env, timeout=900)
+    assert res.returncode == 0, res.stdout[-2000:] + res.stderr[-4000:]
+    assert "RANK_OK 0" in res.stdout and "RANK_OK 1" in res.stdout
 
 
 def test_rare_paths(pkg, orc_mod, oracle, gpu):
@@ -209,7 +375,7 @@ def test_rare_paths(pkg, orc_mod, oracle, gpu):
     from test_hostsim import _stress_scenes
     for name, (sph, lgt) in _stress_scenes(pkg).items():
         ref, ctr = oracle.render(sph, lgt, 96, 64, -4.0, 1.0, 8)
-        for opts in ({"engine": 1}, {"engine": 2}, {"accel": 2}):
+        for opts in ({}, {"staging": 1}, {"accel": 2}):
             fb, mx, st = _render(gpu, sph, lgt, 96, 64, -4.0, 1.0, 8, **opts)
             _assert_parity(orc_mod, oracle, ref, fb)
             assert st["rays"] == ctr["rays"] and st["shadow_rays"] == ctr["shadow_rays"], (name, opts)
@@ -302,6 +468,27 @@ def test_host_program_writes_the_reference_ppm(pkg, tmp_path):
     rows = np.frombuffer(zlib.decompress(data[41:41 + n]), np.uint8).reshape(180, 320 * 3 + 1)
     ppm = (tmp_path / "synth0.ppm").read_bytes()
     assert rows[:, 1:].tobytes() == ppm[ppm.index(b"255\n") + 4:]
+
+
+def test_host_program_animation_and_scene_file(pkg, oracle, tmp_path):
+    """`rt_gamma --frames F --zoom-step dz --scene file`: the multi-frame loop with the scene resident and
+    the readback of frame f overlapping the render of frame f+1 — every frame written
+    equals the oracle's frame at that zoom."""
+    import subprocess
+    sph, lgt = pkg.synth_scene(80, 4, seed=12)
+    scene = tmp_path / "scene.txt"
+    pkg.save_scene(scene, sph, lgt)
+    W, H, S, F, dz = 144, 81, 7, 4, -0.75
+    res = subprocess.run([str(pkg.HOST_BIN), "--scene", str(scene), "--width", str(W), "--height", str(H), "--alias", "1",
+                          "--depth", str(S), "--frames", str(F), "--zoom-step", str(dz), "--out", str(tmp_path / "f_%02d.ppm")],
+                         capture_output=True, text=True, timeout=600)
+    assert res.returncode == 0, res.stdout + res.stderr
+    assert f"{F} frames in" in res.stdout
+    for f in range(F):
+        data = (tmp_path / f"f_{f:02d}.ppm").read_bytes()
+        ref, _ = oracle.render(sph, lgt, W, H, -4.0 + f * dz, 1.0, S)
+        want = oracle.quantise(ref, oracle.max_colour(ref))
+        assert data == b"P6\n%d %d\n255\n" % (W, H) + want.tobytes(), f
 
 
 def test_reference_structs_through_the_abi(pkg, tmp_path):
