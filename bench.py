@@ -401,8 +401,10 @@ def run_ours(args):
             finish_e2e(1)
             barrier()
             t0 = time.perf_counter()
+            marks = []
             for k in range(args.steps):
                 step_e2e(k)
+                marks.append(time.perf_counter() - t0)
             finish_e2e(args.steps)
             barrier()
             e2e_s = time.perf_counter() - t0
@@ -413,6 +415,7 @@ def run_ours(args):
         e2e = {"value": rays * args.steps / e2e_s / 1e6, "unit": "Mrays/s",
                "h2d_bytes_per_step": int(sph.nbytes + lgt.nbytes) * G, "d2h_bytes_per_step": int(frame_bytes),
                "frames_per_s": args.steps / e2e_s, "ms_per_step": e2e_s / args.steps * 1e3,
+               "host_time_after_each_step_ms": [round(m * 1e3, 2) for m in marks],
                "path": "rt_cuda_upload_scene (host AoS) -> rt_cuda_render -> rt_cuda_readback_rgb8_async (pinned host "
                        "double buffer; the copy of frame k overlaps the render of frame k+1) -> rt_cuda_readback_wait"
                        if G == 1 else

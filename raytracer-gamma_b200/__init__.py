@@ -20,10 +20,14 @@ import numpy as np
 
 PKG_DIR = Path(__file__).resolve().parent
 REPO_ROOT = PKG_DIR.parent
-LIB_PATH = Path(os.environ.get("RTG_LIB", PKG_DIR / "librt_cuda.so"))   # RTG_LIB: development override
-SCENE_LIB_PATH = PKG_DIR / "librt_scene.so"          # host-only: scene builders (no CUDA in it)
-MULTI_LIB_PATH = PKG_DIR / "librt_cuda_multi.so"     # multi-GPU sequencing over librt_cuda.so + NCCL
-HOST_BIN = PKG_DIR / "rt_gamma"
+# Development overrides: RTG_LIB_DIR = a frozen copy of the built libraries + rt_gamma (scripts/freeze_build.sh;
+# build() then never recompiles), RTG_LIB = another librt_cuda.so only.
+_FROZEN = "RTG_LIB_DIR" in os.environ
+_BIN_DIR = Path(os.environ["RTG_LIB_DIR"]).resolve() if _FROZEN else PKG_DIR
+LIB_PATH = Path(os.environ.get("RTG_LIB", _BIN_DIR / "librt_cuda.so"))
+SCENE_LIB_PATH = _BIN_DIR / "librt_scene.so"         # host-only: scene builders (no CUDA in it)
+MULTI_LIB_PATH = _BIN_DIR / "librt_cuda_multi.so"    # multi-GPU sequencing over librt_cuda.so + NCCL
+HOST_BIN = _BIN_DIR / "rt_gamma"
 
 # Layout of the reference PODs (sphere.h:9-14, raytracer.h:20-25, vec.h:27-29)
 SPHERE_DTYPE = np.dtype(
@@ -45,6 +49,9 @@ def _stale(out: Path, deps) -> bool:
 def build(force: bool = False, verbose: bool = False) -> Path:
     """Compile in-tree: librt_scene.so (gcc, host only), librt_cuda.so (nvcc, sm_100a),
     librt_cuda_multi.so (NCCL sequencing) and the C++ host program rt_gamma."""
+    if _FROZEN:
+        return LIB_PATH
+
     def run(cmd):
         if verbose:
             print(" ".join(map(str, cmd)))
@@ -100,7 +107,8 @@ class Stats(ctypes.Structure):
         ("kernel_launches", ctypes.c_uint32),
         ("grid", ctypes.c_uint32), ("block", ctypes.c_uint32), ("smem_bytes", ctypes.c_uint32),
         ("staging", ctypes.c_uint32), ("engine", ctypes.c_uint32),
-        ("accel", ctypes.c_uint32), ("clusters", ctypes.c_uint32), ("reserved_", ctypes.c_uint32),
+        ("accel", ctypes.c_uint32), ("clusters", ctypes.c_uint32), ("slots_on_chip", ctypes.c_uint32),
+        ("migrated_slots", ctypes.c_uint32), ("sparse_queries", ctypes.c_uint64),
     ]
 
     def as_dict(self) -> dict:

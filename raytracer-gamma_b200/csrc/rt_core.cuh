@@ -31,6 +31,7 @@
 
 #include <stdint.h>
 #include <math.h>
+#include <string.h>
 
 #if defined(__CUDACC__)
 #define RT_HD __host__ __device__ __forceinline__
@@ -187,6 +188,42 @@ RT_HD bool make_dir(DirQ& D, V3 o, V3 d) {
   return true;
 }
 
+/* The filter's direction only has to be unit length to within the bound's "unit scaling" share
+ * (see Filter): two cheaper set-ups than make_dir's IEEE division and square root.
+ *  - make_dir_fast: d' = d * rsqrt(d.d) with the hardware approximation (MUFU.RSQ, relative error
+ *    <= 2^-22.9 by the PTX ISA): |d'|^2 = 1 +- 12u (2 x 4.3u for the approximation, 2u for the rounded
+ *    d.d, 2u for the three products), i.e. (d'.delta)^2 is off by <= 12u |delta|^2 <= 24u(|o|^2+|c|^2)
+ *    where make_dir's share was 16u: the total first-order bound grows from ~92u to ~100u, kappa = 128u.
+ *  - make_dir_unit: d is already the reference's own normalised vector (vec.h:41: |d|^2 = 1 +- 3u),
+ *    used as it is.
+ * A direction whose squared length is zero, subnormal, infinite or NaN is never filtered: zero is the
+ * reference's certain miss (returns false), everything else goes through the exact test (D.od = NaN
+ * makes dir_filterable fail). */
+RT_HD float rsqrt_fast(float a) {
+#if defined(__CUDA_ARCH__)
+  float r; asm("rsqrt.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(a)); return r;
+#else
+  return 1.f / sqrtf(a);
+#endif
+}
+RT_HD bool make_dir_fast(DirQ& D, V3 o, V3 d) {
+  const float A = vdot(d, d);
+  if (A == 0.f) { D.ndx = D.ndy = D.ndz = 0.f; D.od = 0.f; return false; }
+  const float s = rsqrt_fast(A);
+  const float ux = ex_mul(d.x, s), uy = ex_mul(d.y, s), uz = ex_mul(d.z, s);
+  D.ndx = -ux; D.ndy = -uy; D.ndz = -uz;
+  D.od = fast_fma(uz, o.z, fast_fma(uy, o.y, ex_mul(ux, o.x)));
+  if (!(A >= 1.17549435e-38f && A <= 3.0e38f)) D.od = HUGE_VALF;   /* not filterable: exact test against every sphere */
+  return true;
+}
+RT_HD void make_dir_unit(DirQ& D, V3 o, V3 d) {
+  D.ndx = -d.x; D.ndy = -d.y; D.ndz = -d.z;
+  D.od = fast_fma(d.z, o.z, fast_fma(d.y, o.y, ex_mul(d.x, o.x)));
+  /* vnorm of a denormal / overflowing vector is not unit: such a ray is tested exactly (8u = the bound's share) */
+  const float A = fast_fma(d.z, d.z, fast_fma(d.y, d.y, ex_mul(d.x, d.x)));
+  if (!(fabsf(A - 1.f) <= 4.76837158e-07f)) D.od = HUGE_VALF;
+}
+
 /* origin term of the cluster pass: q(1-kappa)(1-2^-12), see "Cluster filter" */
 RT_HD OriginQ cluster_origin(const OriginQ& O) {
   OriginQ C = O;
@@ -255,13 +292,16 @@ RT_HD bool contains_exact(float4_ g, V3 p) {
 /* ---- suspended calls -------------------------------------------------------- */
 #define RT_MAX_STACK 16
 #define RT_SHADOW_BATCH 4
-struct Frame {            /* 16 words: one 64-byte local-memory record */
+struct Frame {            /* 13 words */
   V3 colour;              /* cur.colour at suspension                                  */
-  float stage;            /* 1.f: waiting for the refracted child, 2.f: reflected child */
-  V3 reflCol; float medium;   /* reflection intensity (raytracer.h:563-578), medium id  */
-  V3 reflO; float pad0;   /* pre-computed reflected ray (raytracer.h:817-842)           */
-  V3 reflD; float pad1;
+  V3 reflCol;             /* reflection intensity (raytracer.h:563-578)                */
+  V3 reflO;               /* pre-computed reflected ray (raytracer.h:817-842)           */
+  V3 reflD;
+  int tag;                /* stage << 16 | medium: stage 1 waits for the refracted child, 2 for the reflected one */
 };
+RT_HD int frame_tag(int stage, int medium) { return (stage << 16) | medium; }
+RT_HD int frame_stage(const Frame& f) { return f.tag >> 16; }
+RT_HD int frame_medium(const Frame& f) { return f.tag & 0xFFFF; }
 
 struct Counters {         /* per-lane tallies, reduced per block at the end */
   uint32_t rays, shadow, containQ, containT, exactTests, samples;
@@ -293,6 +333,58 @@ struct Slot {
 };
 /* The suspended calls of a slot live beside it: Frame stack[RT_MAX_STACK] (only the slot
  * record is small enough to be copied into registers while it is advanced). */
+
+/* ---- slot records: how a slot is kept between two passes (21 words) ------------------------
+ * word 0      pixel (index of the sample's result record, 0xFFFFFFFF = free slot)
+ * word 1      kind | ndirs << 2 | (top + 1) << 5 | light << 10
+ * word 2      medium | obj << 16
+ * words 3..   result, rayD, rayI, P, Nrm, lit|colour (3 words each).  While a TRACE query is pending the
+ *             hit fields are dead and the P words hold the ray's origin; the probe point of a CONTAIN
+ *             query is P + 0.01 rayD (raytracer.h:688-692), rebuilt when the record is read.  The call's
+ *             colour is zero from its start until the matte term is added (raytracer.h:468-484), i.e.
+ *             whenever a TRACE or SHADOW query is pending, and the matte sum `lit` is dead once it has
+ *             been added: the two share their words (lit while SHADOW is pending, colour while CONTAIN is).
+ * The answer of the query (minT / hitIdx / blocked) is not part of the record: the pass hands it over in
+ * registers.  STRIDE = distance in words between consecutive record words (1, or the CTA size when the
+ * records of a CTA are interleaved in shared memory). */
+#define RT_SLOT_WORDS 21
+enum { W_PIXEL = 0, W_HDR = 1, W_MEDOBJ = 2, W_RESULT = 3, W_RAYD = 6, W_RAYI = 9, W_P = 12, W_NRM = 15, W_LITCOL = 18 };
+#if defined(__CUDA_ARCH__)
+RT_HD uint32_t f2u(float f) { return __float_as_uint(f); }
+RT_HD float u2f(uint32_t u) { return __uint_as_float(u); }
+#else
+RT_HD uint32_t f2u(float f) { uint32_t u; memcpy(&u, &f, 4); return u; }
+RT_HD float u2f(uint32_t u) { float f; memcpy(&f, &u, 4); return f; }
+#endif
+template <int STRIDE> RT_HD V3 rec_ldv(const uint32_t* r, int wd) {
+  return mk(u2f(r[wd * STRIDE]), u2f(r[(wd + 1) * STRIDE]), u2f(r[(wd + 2) * STRIDE]));
+}
+template <int STRIDE> RT_HD void rec_stv(uint32_t* r, int wd, V3 v) {
+  r[wd * STRIDE] = f2u(v.x); r[(wd + 1) * STRIDE] = f2u(v.y); r[(wd + 2) * STRIDE] = f2u(v.z);
+}
+template <int STRIDE> RT_HD void slot_pack(uint32_t* r, const Slot& s) {
+  r[W_PIXEL * STRIDE] = s.pixel;
+  r[W_HDR * STRIDE] = (uint32_t)s.kind | ((uint32_t)s.ndirs << 2) | ((uint32_t)(s.top + 1) << 5) | ((uint32_t)s.light << 10);
+  r[W_MEDOBJ * STRIDE] = ((uint32_t)s.medium & 0xFFFFu) | ((uint32_t)s.obj << 16);
+  rec_stv<STRIDE>(r, W_RESULT, s.result);
+  rec_stv<STRIDE>(r, W_RAYD, s.rayD); rec_stv<STRIDE>(r, W_RAYI, s.rayI);
+  rec_stv<STRIDE>(r, W_P, (s.kind == K_TRACE) ? s.qo : s.P);
+  rec_stv<STRIDE>(r, W_NRM, s.Nrm);
+  rec_stv<STRIDE>(r, W_LITCOL, (s.kind == K_CONTAIN) ? s.colour : s.lit);
+}
+template <int STRIDE> RT_HD void slot_unpack(const uint32_t* r, Slot& s) {
+  s.pixel = r[W_PIXEL * STRIDE];
+  const uint32_t h = r[W_HDR * STRIDE], mo = r[W_MEDOBJ * STRIDE];
+  s.kind = (int)(h & 3u); s.ndirs = (int)((h >> 2) & 7u); s.top = (int)((h >> 5) & 31u) - 1; s.light = (int)(h >> 10);
+  s.medium = (int)(mo & 0xFFFFu); s.obj = (int)(mo >> 16);
+  s.result = rec_ldv<STRIDE>(r, W_RESULT);
+  s.rayD = rec_ldv<STRIDE>(r, W_RAYD); s.rayI = rec_ldv<STRIDE>(r, W_RAYI);
+  s.P = rec_ldv<STRIDE>(r, W_P); s.Nrm = rec_ldv<STRIDE>(r, W_NRM);
+  const V3 lc = rec_ldv<STRIDE>(r, W_LITCOL), zero = mk(0.f, 0.f, 0.f);
+  s.colour = (s.kind == K_CONTAIN) ? lc : zero;
+  s.lit = (s.kind == K_CONTAIN) ? zero : lc;
+  s.qo = (s.kind == K_CONTAIN) ? vadd(vscale(0.01f, s.rayD), s.P) : s.P;
+}
 
 struct Camera {           /* main.cpp:384-402, evaluated once on the host in float */
   uint32_t W, H;
@@ -393,15 +485,15 @@ RT_HD bool unwind(Slot& s, Frame* stack, Counters& ctr, const Camera& cam) {
     Frame& f = stack[s.top];
     --s.top;
     s.colour = vadd(s.result, f.colour);
-    if (f.stage == 1.f) {
+    if (frame_stage(f) == 1) {
       if (significant(f.reflCol)) {
         /* re-push as stage 2 (always fits: the slot was just vacated) */
         ++s.top;
-        f.colour = s.colour; f.stage = 2.f;
+        f.colour = s.colour; f.tag = frame_tag(2, frame_medium(f));
         s.result = s.colour;
         if (s.top < cam.S - 1) {
           /* reflected child, raytracer.h:602-611 */
-          s.rayD = f.reflD; s.rayI = f.reflCol; s.medium = (int)f.medium;
+          s.rayD = f.reflD; s.rayI = f.reflCol; s.medium = frame_medium(f);
           s.colour = mk(0.f, 0.f, 0.f);
           set_trace_query(s, ctr, f.reflO, f.reflD);
           return false;
@@ -497,8 +589,8 @@ RT_HD int after_contain(Slot& s, Frame* stack, Counters& ctr, const SceneView& s
   /* suspend (always fits: depth <= S-1) */
   ++s.top;
   Frame& f = stack[s.top];
-  f.colour = s.colour; f.stage = 1.f;
-  f.reflCol = rc; f.medium = (float)s.medium;
+  f.colour = s.colour; f.tag = frame_tag(1, s.medium);
+  f.reflCol = rc;
   if (significant(rc)) {
     /* raytracer.h:817-842 */
     const float perp = ex_mul(2.f, vdot(s.rayD, s.Nrm));

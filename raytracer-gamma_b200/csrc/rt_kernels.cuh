@@ -8,6 +8,15 @@
  * quantise_kernel  float4 framebuffer + max -> RGB8 (main.cpp:71-76)
  * assemble_rgb8_kernel  multi-GPU strip de-interleave
  *
+ * State.  A sample in flight is a 24-word SLOT RECORD (the call being evaluated: result, colour, ray
+ * direction / intensity, hit point, normal, matte sum, three header words).  The records of a CTA live
+ * ON CHIP in shared memory, word-major (record word w of slot k of thread t at ((k*24+w)*256+t) words:
+ * conflict-free), whenever they fit beside the filter records (SMEM_SLOTS; up to ~1 700 spheres with
+ * three slots per lane); larger scenes and the accelerated mode keep them in local memory.  The
+ * suspended calls (raytraceStack.h:13-68) are 13-word frames in local memory; a lane's census of its
+ * slots' pending queries is one register.  The answer of a query (closest hit / occlusion bits /
+ * container) never touches memory: the pass hands it to the state machine in registers.
+ *
  * One pass of trace_kernel (per warp, all lanes converged throughout):
  *   refill   free slots take the next samples from a tile queue (one global atomicAdd
  *            per warp granule, __ballot_sync ranks the takers)
@@ -15,13 +24,14 @@
  *            picks the kind that fills most lanes (__reduce_add_sync)
  *   filter   the chosen kind's loop over ALL spheres, sphere records staged once per
  *            CTA into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier) or
- *            read from __constant__ for small scenes:
+ *            read from the constant bank (launch parameter) for small scenes:
  *              trace    2 rays per lane    (1 LDS.128 + 7 FFMA2 + FADD2 + 2 SHF) per sphere
  *              shadow   4 rays, one origin (1 LDS.128 + 3 FFMA + FADD + 2 x [4 FFMA2 + 2 SHF])
  *              contain  2 probes per lane  (1 LDS.128 + 3 FFMA2 + FADD2 + 2 SHF)
  *            (packed FP32 pairs: one FFMA2 serves both rays) — each test leaves one SIGN BIT
  *            (certain miss or not) in the group's funnel-shifted register
- *   gather   set bits become (sub-query, sphere) entries in a per-lane shared-memory list
+ *   gather   set bits become (sub-query, sphere) entries in a per-lane shared-memory list; a list
+ *            that fills up is resolved and the loop RESUMES where that lane stopped (no fallback)
  *   resolve  k-th entries of all lanes go through the reference's exact expressions together
  *   advance  the served slots take their O(1) shading / state transition (one kind per
  *            pass, so the lanes agree on the path)
@@ -39,11 +49,8 @@ namespace rtg {
 #define RT_BLOCK 256
 #endif
 #define RT_LIST_MAX 24
-/* accelerated mode: its loops run over an eighth of the records, so smaller unrolled groups and a single
- * shadow instance (fewer instructions to fetch per pass) win: 41.9 -> 38.8 ms at 4K / 1 024 spheres */
-#ifndef RT_ACCEL_ONE_SHADOW
-#define RT_ACCEL_ONE_SHADOW 1
-#endif
+/* accelerated mode: its loops run over an eighth of the records, so smaller unrolled groups
+ * (fewer instructions to fetch per pass) win: 41.9 -> 38.8 ms at 4K / 1 024 spheres */
 #ifndef RT_GROUP_TA
 #define RT_GROUP_TA 8
 #endif
@@ -60,6 +67,13 @@ namespace rtg {
 #define RT_CONST_MAX_SPHERES 1024
 #define RT_NUM_COUNTERS 24
 #define RT_NO_PIXEL 0xFFFFFFFFu
+#ifndef RT_ADV_CONVERGENT
+#define RT_ADV_CONVERGENT 1      /* write the slot record back after the warp has reconverged (see advance_slot) */
+#endif
+#ifndef RT_SHADOW_INLINE_NORM
+#define RT_SHADOW_INLINE_NORM 1  /* the four normalisations of a shadow batch inline (they overlap) rather than out of line */
+#endif
+#define RT_SLOTS 4               /* slots per lane (3 in shared memory when 4 do not fit beside the filter records) */
 
 struct TraceParams {
   SceneView sc;
@@ -74,7 +88,8 @@ struct TraceParams {
   uint32_t stripRows, stripFirst, stripStride;   /* row r is ours iff (r/stripRows)%stripStride==stripFirst */
   uint32_t tilesX, totalWork, chunk;
   int noFilter;             /* debug: exact test for every sphere                   */
-  int prefetch;             /* prefetch served slots' state into L1 before the sphere loop */
+  int rebalance;            /* drain balancing on (default) / off (option "rebalance")   */
+  uint32_t sparseBelow;     /* a drained warp with at most this many queries left serves them in sparse rounds (0 = never) */
   uint32_t list1Max;        /* accelerated mode: capacity of the per-lane (sub, cluster) lists */
 };
 
@@ -138,6 +153,22 @@ __device__ __forceinline__ bool work_to_task(const TraceParams& p, uint32_t idx,
   return true;
 }
 
+/* ---- slot storage: the 21-word records of rt_core.cuh (slot_pack / slot_unpack), either interleaved in
+ * shared memory (record word w of slot k of thread t at ((k*21+w)*256+t) words: conflict-free) or in the
+ * thread's local memory ---- */
+template <bool SMEM>
+struct SlotStore {
+  static constexpr int STRIDE = SMEM ? RT_BLOCK : 1;
+  uint32_t* base;      /* shared memory (already offset by the thread index) or the thread's local array */
+  __device__ __forceinline__ uint32_t* rec(int k) const { return base + k * RT_SLOT_WORDS * STRIDE; }
+  __device__ __forceinline__ uint32_t& at(int k, int wd) const { return base[(k * RT_SLOT_WORDS + wd) * STRIDE]; }
+  __device__ __forceinline__ V3 ldv(int k, int wd) const { return rec_ldv<STRIDE>(rec(k), wd); }
+};
+template <class St>
+__device__ __forceinline__ void store_slot(const St& st, int k, const Slot& s) { slot_pack<St::STRIDE>(st.rec(k), s); }
+template <class St>
+__device__ __forceinline__ void load_slot(const St& st, int k, Slot& s) { slot_unpack<St::STRIDE>(st.rec(k), s); }
+
 /* Per-warp state shared by the passes. */
 struct WarpCtx {
 #ifdef RT_PHASE_TIMING
@@ -145,12 +176,11 @@ struct WarpCtx {
   long long phase[6];       /* tail (cycles after the queue ran dry), set-up, filter loop, resolve, advance, longest tail */
   long long tDry;
 #endif
-  const float4* filt;       /* filter records (shared memory, or unused with __constant__); accelerated mode: cluster records */
+  const float4* filt;       /* filter records (shared memory, or unused with the constant bank); accelerated mode: cluster records */
   const float4* mfilt;      /* accelerated mode: the clusters' member records (shared memory) */
   const unsigned short* midx;   /* accelerated mode: the members' sphere indices (shared memory) */
   unsigned short* list1;    /* accelerated mode: per-lane (sub, cluster) lists: list1[k * RT_BLOCK + tid] */
   unsigned short* list;     /* per-lane candidate lists: list[k * RT_BLOCK + tid]          */
-  float* geo;               /* per-lane shadow-batch rays of the current pass: geo[w * RT_BLOCK + tid], 16 words */
   uint32_t tid;
   uint32_t nPad;
 };
@@ -175,8 +205,8 @@ __device__ __forceinline__ float4_ load_filt(const WarpCtx& w, const ConstRecord
 typedef unsigned long long f32x2;
 __device__ __forceinline__ f32x2 pk(float lo, float hi) { f32x2 r; asm("mov.b64 %0, {%1,%2};" : "=l"(r) : "f"(lo), "f"(hi)); return r; }
 __device__ __forceinline__ f32x2 pk1(float x) { return pk(x, x); }
-__device__ __forceinline__ float lo_of(f32x2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return a; }
-__device__ __forceinline__ float hi_of(f32x2 v) { float a, b; asm("mov.b64 {%0,%1}, %2;" : "=f"(a), "=f"(b) : "l"(v)); return b; }
+__device__ __forceinline__ float lo_of(f32x2 v) { float a; asm("{ .reg .f32 t; mov.b64 {%0,t}, %1; }" : "=f"(a) : "l"(v)); return a; }
+__device__ __forceinline__ float hi_of(f32x2 v) { float b; asm("{ .reg .f32 t; mov.b64 {t,%0}, %1; }" : "=f"(b) : "l"(v)); return b; }
 __device__ __forceinline__ f32x2 fma2(f32x2 a, f32x2 b, f32x2 c) { f32x2 d; asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(d) : "l"(a), "l"(b), "l"(c)); return d; }
 __device__ __forceinline__ f32x2 sub2(f32x2 a, f32x2 b) { f32x2 d; asm("sub.rn.f32x2 %0, %1, %2;" : "=l"(d) : "l"(a), "l"(b)); return d; }
 struct Origin2 { f32x2 px, py, pz, nq; };
@@ -202,9 +232,6 @@ __device__ __forceinline__ f32x2 bq2(const Dir2& D, f32x2 cx, f32x2 cy, f32x2 cz
 #ifndef RT_GROUP_S4
 #define RT_GROUP_S4 8
 #endif
-#ifndef RT_GROUP_S2
-#define RT_GROUP_S2 16
-#endif
 #ifndef RT_GROUP_C
 #define RT_GROUP_C 16
 #endif
@@ -215,8 +242,7 @@ __device__ __forceinline__ f32x2 bq2(const Dir2& D, f32x2 cx, f32x2 cy, f32x2 cz
  * After the group, test (j, sub) sits at bit G*ND-1 - (j*ND + sub).  mask_of_sub gives the bits
  * of one sub-query; gather turns the set bits of ~signs & mask into list entries
  * (sub << 14 | sphere): scanning from the top bit yields each sub-query's spheres in
- * increasing order.  A full list sets `overflow`: that lane then resolves the pass exactly
- * against every sphere (rare). */
+ * increasing order. */
 template <int ND, int G>
 __host__ __device__ constexpr unsigned mask_of_sub(int sub) {
   unsigned m = 0u;
@@ -227,25 +253,24 @@ __host__ __device__ constexpr unsigned mask_of_sub(int sub) {
  * predicates / the constant bank on every trip, which costs issue slots in the hot loops) */
 __device__ __forceinline__ unsigned pin(unsigned v) { asm volatile("" : "+r"(v)); return v; }
 
+#define RT_FULL 0xFFFFFFFFu
+#define RT_NONE 0xFFFFFFFFu
+
+/* Append the flagged tests of one group to the lane's list; returns the bits that did not fit. */
 template <int ND, int G>
-__device__ __forceinline__ void gather(const WarpCtx& w, unsigned comb, uint32_t base, int& cnt,
-                                       bool& overflow) {
+__device__ __forceinline__ unsigned gather(const WarpCtx& w, unsigned comb, uint32_t base, int& cnt) {
   static_assert(G * ND <= 32 && (ND & (ND - 1)) == 0, "one 32-bit register per group");
   while (comb) {
+    if (cnt >= RT_LIST_MAX) return comb;
     const int b = 31 - __clz(comb);
     comb &= ~(1u << b);
-    if (cnt < RT_LIST_MAX) {
-      const uint32_t idx = (uint32_t)(G * ND - 1 - b);
-      const uint32_t sub = idx % ND, j = idx / ND;
-      w.list[cnt * RT_BLOCK + w.tid] = (unsigned short)((sub << 14) | (base + j));
-      ++cnt;
-    } else {
-      overflow = true;
-    }
+    const uint32_t idx = (uint32_t)(G * ND - 1 - b);
+    const uint32_t sub = idx % ND, j = idx / ND;
+    w.list[cnt * RT_BLOCK + w.tid] = (unsigned short)((sub << 14) | (base + j));
+    ++cnt;
   }
+  return 0u;
 }
-
-#define RT_FULL 0xFFFFFFFFu
 
 /* Optional phase timing (development builds, -DRT_PHASE_TIMING): wall cycles a warp spends in
  * each phase of a pass, accumulated into counters[16..21]. */
@@ -255,283 +280,296 @@ __device__ __forceinline__ void gather(const WarpCtx& w, unsigned comb, uint32_t
 #define RT_TICK(slot) do { } while (0)
 #endif
 
-/* Cold path (list overflow, non-finite geometry, no_filter debug mode): answer the slot's
- * pending query with the exact test against every sphere.  Out of line; returns the
- * number of exact tests. */
-__device__ __noinline__ uint32_t exact_all(const SceneView sc, Slot* s, unsigned subs) {
-  uint32_t tests = 0;
-  if (s->kind == K_TRACE) {
-    float t = 1000.f; int h = -1;
-    DirQ D;
-    if (make_dir(D, s->qo, s->rayD)) {
-      for (uint32_t i = 0; i < sc.n; ++i) resolve_trace(t, h, s->qo, s->rayD, sc.geo[i], i);
-      tests = sc.n;
+/* The filter loop of one pass with its candidate lists.  `signs(base)` runs one unrolled group and
+ * returns its sign register; `resolve(entry)` puts one list entry through the exact expressions.
+ * A lane whose list is full stops gathering, remembers where (group and left-over bits), and after
+ * the warp has resolved its lists the loop resumes from the earliest such group with only the
+ * unfinished lanes gathering: any number of candidates is handled, nothing falls back to testing
+ * every sphere exactly.  (Entries are idempotent under re-resolution, and none is resolved twice.) */
+template <int ND, int G, class Signs, class Resolve>
+__device__ __forceinline__ void filter_rounds(WarpCtx& w, uint32_t nPad, unsigned msk, Signs signs, Resolve resolve) {
+  /* first round, the common case: nothing but the loop and the append */
+  int cnt = 0;
+  uint32_t ovAt = RT_NONE;
+  unsigned ovLeft = 0u;
+  for (uint32_t base = 0; base < nPad; base += G) {
+    const unsigned comb = ~signs(base) & msk;
+    if (comb) {
+      const unsigned left = gather<ND, G>(w, comb, base, cnt);
+      if (left && ovAt == RT_NONE) { ovAt = base; ovLeft = left; }     /* list full: remember where */
     }
-    s->minT = t; s->hitIdx = h;
-  } else if (s->kind == K_SHADOW) {
-    unsigned blocked = s->blocked;
-    ShadowGeo sg;
-    shadow_geo(*s, sc, sg);
-    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
-      if ((subs >> k) & 1u) {
-        blocked &= ~(1u << k);
-        for (uint32_t i = 0; i < sc.n; ++i) {
-          ++tests;
-          if (resolve_shadow(s->P, sg.d[k], sg.gap[k], sc.geo[i])) { blocked |= 1u << k; break; }
-        }
+  }
+  for (;;) {
+    const int maxc = __reduce_max_sync(RT_FULL, cnt);
+    RT_TICK(2);
+#pragma unroll 1
+    for (int k = 0; k < maxc; ++k)
+      if (k < cnt) resolve((uint32_t)w.list[k * RT_BLOCK + w.tid]);
+    RT_TICK(3);
+    if (!__any_sync(RT_FULL, ovAt != RT_NONE)) break;
+    /* rare: resume from the earliest unfinished group; lanes that finished (RT_NONE) gather nothing more */
+    const uint32_t myFrom = ovAt;
+    const unsigned myMask = ovLeft;
+    const uint32_t start = __reduce_min_sync(RT_FULL, ovAt);
+    cnt = 0; ovAt = RT_NONE; ovLeft = 0u;
+#pragma unroll 1
+    for (uint32_t base = start; base < nPad; base += G) {
+      unsigned comb = ~signs(base) & msk;
+      if (base == myFrom) comb &= myMask;
+      if (comb && base >= myFrom && ovAt == RT_NONE) {
+        const unsigned left = gather<ND, G>(w, comb, base, cnt);
+        if (left) { ovAt = base; ovLeft = left; }
       }
     }
-    s->blocked = blocked;
-  } else if (s->kind == K_CONTAIN) {
-    int h = -1;
-    for (uint32_t i = 0; i < sc.n && h < 0; ++i) { ++tests; resolve_contain(h, s->qo, sc.geo[i], i); }
-    s->hitIdx = h;
   }
-  return tests;
 }
 
+/* ---- cold paths (non-finite geometry, the no_filter debug mode): the exact test against every
+ * sphere, out of line ---- */
+__device__ __noinline__ void exact_trace(const SceneView sc, V3 o, V3 d, float* tOut, int* hOut, uint32_t* tests) {
+  float t = 1000.f; int h = -1;
+  for (uint32_t i = 0; i < sc.n; ++i) resolve_trace(t, h, o, d, sc.geo[i], i);
+  *tests += sc.n;
+  *tOut = t; *hOut = h;
+}
+__device__ __noinline__ bool exact_shadow(const SceneView sc, V3 o, V3 d, float gap, uint32_t* tests) {
+  for (uint32_t i = 0; i < sc.n; ++i) {
+    ++*tests;
+    if (resolve_shadow(o, d, gap, sc.geo[i])) return true;
+  }
+  return false;
+}
+__device__ __noinline__ int exact_contain(const SceneView sc, V3 pnt, uint32_t* tests) {
+  int h = -1;
+  for (uint32_t i = 0; i < sc.n && h < 0; ++i) { ++*tests; resolve_contain(h, pnt, sc.geo[i], i); }
+  return h;
+}
+
+/* What a pass hands to the state machine (registers, never memory). */
+struct Answer { float t; int h; unsigned blocked; };
+
 /* ---- trace pass: up to two rays per lane ---------------------------------------- */
-template <bool USE_CONST>
-__device__ __forceinline__ void pass_trace(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
-                                           int s1, Counters& ctr) {
+template <bool USE_CONST, class St>
+__device__ __forceinline__ void pass_trace(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, const St& st,
+                                           int s0, int s1, Counters& ctr, Answer& a0, Answer& a1) {
   constexpr int G = RT_GROUP_T;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
   DirQ D0, D1;
   D0.ndx = D0.ndy = D0.ndz = D0.od = 0.f; D1 = D0;
   bool live0 = false, live1 = false, exact0 = false, exact1 = false;
   if (s0 >= 0) {
-    O0 = make_origin(slots[s0].qo);
-    live0 = make_dir(D0, slots[s0].qo, slots[s0].rayD);
+    const V3 o = st.ldv(s0, W_P), d = st.ldv(s0, W_RAYD);
+    O0 = make_origin(o);
+    live0 = make_dir_fast(D0, o, d);
     exact0 = live0 && (p.noFilter || !(origin_filterable(O0) && dir_filterable(D0)));
   }
   if (s1 >= 0) {
-    O1 = make_origin(slots[s1].qo);
-    live1 = make_dir(D1, slots[s1].qo, slots[s1].rayD);
+    const V3 o = st.ldv(s1, W_P), d = st.ldv(s1, W_RAYD);
+    O1 = make_origin(o);
+    live1 = make_dir_fast(D1, o, d);
     exact1 = live1 && (p.noFilter || !(origin_filterable(O1) && dir_filterable(D1)));
   }
   constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
   const unsigned msk = pin(((live0 && !exact0) ? m0 : 0u) | ((live1 && !exact1) ? m1 : 0u));
   const Origin2 OO = pack_origin(O0, O1);
   const Dir2 DD = pack_dir(D0, D1);
-  int cnt = 0;
-  bool overflow = false;
-  RT_TICK(1);
-  if (!p.noFilter) {
-    const uint32_t nPad = pin(w.nPad);
-    for (uint32_t base = 0; base < nPad; base += G) {
-      unsigned k = 0;
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
-        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
-        const f32x2 b = bq2(DD, cx, cy, cz);
-        f32x2 ch = fma2(OO.px, cx, pk1(s.w));
-        ch = fma2(OO.py, cy, ch);
-        ch = fma2(OO.pz, cz, ch);
-        const f32x2 d = fma2(b, b, sub2(OO.nq, ch));     /* both rays: sign set <=> certain miss */
-        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
-        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
-      }
-      const unsigned comb = ~k & msk;
-      if (comb) gather<2, G>(w, comb, base, cnt, overflow);
-    }
-  }
   float t0 = 1000.f, t1 = 1000.f;
   int h0 = -1, h1 = -1;
-  const int maxc = __reduce_max_sync(RT_FULL, cnt);
-  RT_TICK(2);
-#pragma unroll 1
-  for (int k = 0; k < maxc; ++k) {
-    if (k < cnt && !overflow) {
-      const uint32_t e = w.list[k * RT_BLOCK + w.tid];
-      const uint32_t i = e & 0x3FFFu, sub = e >> 14;
-      if (i < p.sc.n) {
-        ctr.exactTests++;
-        const Slot& q = slots[sub ? s1 : s0];
-        const float t = ray_sphere_t(p.sc.geo[i], q.qo, q.rayD);
-        if (t > 0.f) {       /* raytracer.h:166-188; strict <: first index wins ties */
-          if (sub) { if (t < t1) { t1 = t; h1 = (int)i; } }
-          else     { if (t < t0) { t0 = t; h0 = (int)i; } }
+  RT_TICK(1);
+  filter_rounds<2, G>(
+      w, pin(p.noFilter ? 0u : w.nPad), msk,
+      [&](uint32_t base) {
+        unsigned k = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
+          const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
+          const f32x2 b = bq2(DD, cx, cy, cz);
+          f32x2 ch = fma2(OO.px, cx, pk1(s.w));
+          ch = fma2(OO.py, cy, ch);
+          ch = fma2(OO.pz, cz, ch);
+          const f32x2 d = fma2(b, b, sub2(OO.nq, ch));     /* both rays: sign set <=> certain miss */
+          k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+          k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
         }
-      }
-    }
-  }
-  if (overflow) { exact0 = live0; exact1 = live1; }
-  if (s0 >= 0) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
-  if (s1 >= 0) { slots[s1].minT = t1; slots[s1].hitIdx = h1; }
-  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
-  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+        return k;
+      },
+      [&](uint32_t e) {
+        const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+        if (i < p.sc.n) {
+          ctr.exactTests++;
+          const int sl = sub ? s1 : s0;
+          const float t = ray_sphere_t(p.sc.geo[i], st.ldv(sl, W_P), st.ldv(sl, W_RAYD));
+          if (t > 0.f) {       /* raytracer.h:166-188; strict <: first index wins ties */
+            if (sub) { if (t < t1) { t1 = t; h1 = (int)i; } }
+            else     { if (t < t0) { t0 = t; h0 = (int)i; } }
+          }
+        }
+      });
+  if (exact0) exact_trace(p.sc, st.ldv(s0, W_P), st.ldv(s0, W_RAYD), &t0, &h0, &ctr.exactTests);
+  if (exact1) exact_trace(p.sc, st.ldv(s1, W_P), st.ldv(s1, W_RAYD), &t1, &h1, &ctr.exactTests);
+  a0.t = t0; a0.h = h0; a1.t = t1; a1.h = h1;
 }
 
 /* ---- shadow pass: the (up to four) shadow rays of one hit share their origin ------
  * A lane with no shadow batch waiting may bring a TRACE slot instead: a trace ray is the
- * same query with one direction, so it rides along for free and keeps the lane busy. */
-template <bool USE_CONST, int ND>
-__device__ __forceinline__ void pass_shadow(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
-                                            Counters& ctr) {
-  constexpr int G = (ND == 4) ? RT_GROUP_S4 : RT_GROUP_S2;
+ * same query with one direction, so it rides along for free and keeps the lane busy.
+ * The rays of the batch (raytracer.h:279-286: the reference's own normalised vectors) stay in
+ * registers, packed and negated, from the set-up through the loop to resolve and advance. */
+struct ShadowRays { Dir2 DP[RT_SHADOW_BATCH / 2]; float gap[RT_SHADOW_BATCH]; };
+__device__ __forceinline__ V3 shadow_dir(const ShadowRays& r, uint32_t sub) {
+  const Dir2& q = (sub & 2u) ? r.DP[1] : r.DP[0];
+  return (sub & 1u) ? mk(-hi_of(q.ndx), -hi_of(q.ndy), -hi_of(q.ndz)) : mk(-lo_of(q.ndx), -lo_of(q.ndy), -lo_of(q.ndz));
+}
+
+template <bool USE_CONST, class St>
+__device__ __forceinline__ void pass_shadow(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, const St& st,
+                                            int s0, bool asTrace, Counters& ctr, Answer& a0, ShadowRays& R) {
+  constexpr int ND = RT_SHADOW_BATCH;
+  constexpr int G = RT_GROUP_S4;
   OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
   DirQ D[ND];
   unsigned live = 0u, exact = 0u;
-  bool asTrace = false;
+  V3 org = mk(0.f, 0.f, 0.f);
+  V3 riderD = mk(0.f, 0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; }
+  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; R.gap[k] = 0.f; }
   if (s0 >= 0) {
-    /* the batch's rays (or the rider's single ray) go to the lane's shared-memory scratch:
-     * resolve and advance read them back, the slot record does not carry them */
-    asTrace = slots[s0].kind == K_TRACE;
-    ShadowGeo g;
-    V3 org;
-    if (asTrace) {
-      org = slots[s0].qo;
-      g.d[0] = slots[s0].rayD; g.gap[0] = 0.f;
-#pragma unroll
-      for (int k = 1; k < RT_SHADOW_BATCH; ++k) { g.d[k] = mk(0.f, 0.f, 0.f); g.gap[k] = 0.f; }
-    } else {
-      org = slots[s0].P;
-      shadow_geo(slots[s0], p.sc, g);
-    }
-#pragma unroll
-    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
-      w.geo[(4 * k + 0) * RT_BLOCK + w.tid] = g.d[k].x;
-      w.geo[(4 * k + 1) * RT_BLOCK + w.tid] = g.d[k].y;
-      w.geo[(4 * k + 2) * RT_BLOCK + w.tid] = g.d[k].z;
-      w.geo[(4 * k + 3) * RT_BLOCK + w.tid] = g.gap[k];
-    }
+    org = st.ldv(s0, W_P);
     O = make_origin(org);
     const bool ofil = origin_filterable(O);
-    const int nd = slots[s0].ndirs;
+    if (asTrace) {
+      riderD = st.ldv(s0, W_RAYD);
+      if (make_dir_fast(D[0], org, riderD)) {
+        live = 1u;
+        if (p.noFilter || !(ofil && dir_filterable(D[0]))) exact = 1u;
+      }
+    } else {
+      const uint32_t hdr = st.at(s0, W_HDR);
+      const int nd = (int)((hdr >> 2) & 7u), light = (int)(hdr >> 10);
 #pragma unroll
-    for (int k = 0; k < ND; ++k) {
-      if (k < nd && make_dir(D[k], org, g.d[k])) {
-        live |= 1u << k;
-        if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
+      for (int k = 0; k < ND; ++k) {
+        if (k < nd) {
+          const float4_ lp = p.sc.lpos[light + k];
+          const V3 dir = vsub(mk(lp.x, lp.y, lp.z), org);     /* raytracer.h:279-286 */
+          R.gap[k] = vdot(dir, dir);
+#if RT_SHADOW_INLINE_NORM
+          make_dir_unit(D[k], org, vunit_i(dir));       /* independent normalisations: inline so they overlap */
+#else
+          make_dir_unit(D[k], org, vunit(dir));
+#endif
+          live |= 1u << k;
+          if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
+        }
       }
     }
   }
+  R.DP[0] = pack_dir(D[0], D[1]);
+  R.DP[1] = pack_dir(D[2], D[3]);
   unsigned msk = 0u;
 #pragma unroll
   for (int k = 0; k < ND; ++k) msk |= (((live & ~exact) >> k) & 1u) ? mask_of_sub<ND, G>(k) : 0u;
   msk = pin(msk);
-  static_assert(ND % 2 == 0, "rays are processed as packed pairs");
-  Dir2 DP[ND / 2];
-#pragma unroll
-  for (int k = 0; k < ND / 2; ++k) DP[k] = pack_dir(D[2 * k], D[2 * k + 1]);
-  int cnt = 0;
-  bool overflow = false;
-  RT_TICK(1);
-  if (!p.noFilter) {
-    const uint32_t nPad = pin(w.nPad);
-    for (uint32_t base = 0; base < nPad; base += G) {
-      unsigned sk = 0u;
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
-        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
-        const f32x2 e = pk1(ex_sub(O.nq, filter_ch(O, s)));   /* -q - ch: once per sphere, all rays share the origin */
-#pragma unroll
-        for (int k = 0; k < ND / 2; ++k) {
-          const f32x2 b = bq2(DP[k], cx, cy, cz);
-          const f32x2 d = fma2(b, b, e);
-          sk = __funnelshift_l(__float_as_uint(lo_of(d)), sk, 1);
-          sk = __funnelshift_l(__float_as_uint(hi_of(d)), sk, 1);
-        }
-      }
-      const unsigned comb = ~sk & msk;
-      if (comb) gather<ND, G>(w, comb, base, cnt, overflow);
-    }
-  }
   unsigned blocked = 0u;
   float t0 = 1000.f;
   int h0 = -1;
-  const int maxc = __reduce_max_sync(RT_FULL, cnt);
-  RT_TICK(2);
-#pragma unroll 1
-  for (int k = 0; k < maxc; ++k) {
-    if (k < cnt && !overflow) {
-      const uint32_t e = w.list[k * RT_BLOCK + w.tid];
-      const uint32_t i = e & 0x3FFFu, sub = e >> 14;
-      if (i < p.sc.n && !((blocked >> sub) & 1u)) {
-        ctr.exactTests++;
-        const V3 d = mk(w.geo[(4 * sub + 0) * RT_BLOCK + w.tid], w.geo[(4 * sub + 1) * RT_BLOCK + w.tid],
-                        w.geo[(4 * sub + 2) * RT_BLOCK + w.tid]);
-        const V3 org = asTrace ? slots[s0].qo : slots[s0].P;
-        const float t = ray_sphere_t(p.sc.geo[i], org, d);
-        if (t > 0.f) {
-          if (asTrace) {          /* closest hit, raytracer.h:166-188 */
-            if (t < t0) { t0 = t; h0 = (int)i; }
-          } else if (t < 1000.f) { /* occluder iff |t d|^2 < gap, raytracer.h:291-304 (see resolve_shadow) */
-            const V3 dist = vscale(t, d);
-            if (vdot(dist, dist) < w.geo[(4 * sub + 3) * RT_BLOCK + w.tid]) blocked |= 1u << sub;
+  RT_TICK(1);
+  filter_rounds<ND, G>(
+      w, pin(p.noFilter ? 0u : w.nPad), msk,
+      [&](uint32_t base) {
+        unsigned sk = 0u;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
+          const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
+          const f32x2 e = pk1(ex_sub(O.nq, filter_ch(O, s)));   /* -q - ch: once per sphere, all rays share the origin */
+#pragma unroll
+          for (int k = 0; k < ND / 2; ++k) {
+            const f32x2 b = bq2(R.DP[k], cx, cy, cz);
+            const f32x2 d = fma2(b, b, e);
+            sk = __funnelshift_l(__float_as_uint(lo_of(d)), sk, 1);
+            sk = __funnelshift_l(__float_as_uint(hi_of(d)), sk, 1);
           }
         }
-      }
+        return sk;
+      },
+      [&](uint32_t e) {
+        const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+        if (i < p.sc.n && !((blocked >> sub) & 1u)) {
+          ctr.exactTests++;
+          const V3 d = asTrace ? riderD : shadow_dir(R, sub);
+          const float t = ray_sphere_t(p.sc.geo[i], org, d);
+          if (t > 0.f) {
+            if (asTrace) {          /* closest hit, raytracer.h:166-188 */
+              if (t < t0) { t0 = t; h0 = (int)i; }
+            } else if (t < 1000.f) { /* occluder iff |t d|^2 < gap, raytracer.h:291-304 (see resolve_shadow) */
+              const V3 dist = vscale(t, d);
+              const float gp = (sub & 2u) ? ((sub & 1u) ? R.gap[3] : R.gap[2]) : ((sub & 1u) ? R.gap[1] : R.gap[0]);
+              if (vdot(dist, dist) < gp) blocked |= 1u << sub;
+            }
+          }
+        }
+      });
+  if (exact) {
+    if (asTrace) {
+      exact_trace(p.sc, org, riderD, &t0, &h0, &ctr.exactTests);
+    } else {
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        if ((exact >> k) & 1u) {
+          blocked &= ~(1u << k);
+          if (exact_shadow(p.sc, org, shadow_dir(R, (uint32_t)k), R.gap[k], &ctr.exactTests)) blocked |= 1u << k;
+        }
     }
   }
-  if (overflow) exact = live;
-  if (s0 >= 0) {
-    if (asTrace) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
-    else slots[s0].blocked = blocked;
-  }
-  if (exact) ctr.exactTests += exact_all(p.sc, &slots[s0], exact);
+  a0.t = t0; a0.h = h0; a0.blocked = blocked;
 }
 
 /* ---- containment pass: up to two probe points per lane ---------------------------- */
-template <bool USE_CONST>
-__device__ __forceinline__ void pass_contain(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
-                                             int s1, Counters& ctr) {
+template <bool USE_CONST, class St>
+__device__ __forceinline__ void pass_contain(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, const St& st,
+                                             int s0, int s1, Counters& ctr, Answer& a0, Answer& a1) {
   constexpr int G = RT_GROUP_C;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
+  V3 q0 = mk(0.f, 0.f, 0.f), q1 = q0;
   bool exact0 = false, exact1 = false;
-  if (s0 >= 0) { O0 = make_origin(slots[s0].qo); exact0 = p.noFilter || !origin_filterable(O0); }
-  if (s1 >= 0) { O1 = make_origin(slots[s1].qo); exact1 = p.noFilter || !origin_filterable(O1); }
+  if (s0 >= 0) { q0 = vadd(vscale(0.01f, st.ldv(s0, W_RAYD)), st.ldv(s0, W_P)); O0 = make_origin(q0); exact0 = p.noFilter || !origin_filterable(O0); }
+  if (s1 >= 0) { q1 = vadd(vscale(0.01f, st.ldv(s1, W_RAYD)), st.ldv(s1, W_P)); O1 = make_origin(q1); exact1 = p.noFilter || !origin_filterable(O1); }
   constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
   const unsigned msk = pin(((s0 >= 0 && !exact0) ? m0 : 0u) | ((s1 >= 0 && !exact1) ? m1 : 0u));
   const Origin2 OO = pack_origin(O0, O1);
-  int cnt = 0;
-  bool overflow = false;
-  RT_TICK(1);
-  if (!p.noFilter) {
-    const uint32_t nPad = pin(w.nPad);
-    for (uint32_t base = 0; base < nPad; base += G) {
-      unsigned k = 0;
-#pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
-        f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
-        ch = fma2(OO.py, pk1(s.y), ch);
-        ch = fma2(OO.pz, pk1(s.z), ch);
-        const f32x2 d = sub2(OO.nq, ch);                  /* both probes: sign set <=> certainly outside */
-        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
-        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
-      }
-      const unsigned comb = ~k & msk;
-      if (comb) gather<2, G>(w, comb, base, cnt, overflow);
-    }
-  }
   int h0 = -1, h1 = -1;
-  const int maxc = __reduce_max_sync(RT_FULL, cnt);
-  RT_TICK(2);
-#pragma unroll 1
-  for (int k = 0; k < maxc; ++k) {
-    if (k < cnt && !overflow) {
-      const uint32_t e = w.list[k * RT_BLOCK + w.tid];
-      const uint32_t i = e & 0x3FFFu, sub = e >> 14;
-      if (i < p.sc.n) {
-        ctr.exactTests++;
-        const bool in = contains_exact(p.sc.geo[i], slots[sub ? s1 : s0].qo);
-        if (in) {            /* raytracer.h:264: the first container in index order wins */
-          if (sub) { if (h1 < 0) h1 = (int)i; }
-          else     { if (h0 < 0) h0 = (int)i; }
+  RT_TICK(1);
+  filter_rounds<2, G>(
+      w, pin(p.noFilter ? 0u : w.nPad), msk,
+      [&](uint32_t base) {
+        unsigned k = 0;
+#pragma unroll
+        for (int j = 0; j < G; ++j) {
+          const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
+          f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
+          ch = fma2(OO.py, pk1(s.y), ch);
+          ch = fma2(OO.pz, pk1(s.z), ch);
+          const f32x2 d = sub2(OO.nq, ch);                  /* both probes: sign set <=> certainly outside */
+          k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+          k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
         }
-      }
-    }
-  }
-  if (overflow) { exact0 = s0 >= 0; exact1 = s1 >= 0; }
-  if (s0 >= 0) slots[s0].hitIdx = h0;
-  if (s1 >= 0) slots[s1].hitIdx = h1;
-  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
-  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+        return k;
+      },
+      [&](uint32_t e) {
+        const uint32_t i = e & 0x3FFFu, sub = e >> 14;
+        if (i < p.sc.n) {
+          ctr.exactTests++;
+          const bool in = contains_exact(p.sc.geo[i], sub ? q1 : q0);
+          if (in) {            /* raytracer.h:264: the first container in index order wins */
+            if (sub) { if (h1 < 0) h1 = (int)i; }
+            else     { if (h0 < 0) h0 = (int)i; }
+          }
+        }
+      });
+  if (exact0) h0 = exact_contain(p.sc, q0, &ctr.exactTests);
+  if (exact1) h1 = exact_contain(p.sc, q1, &ctr.exactTests);
+  a0.h = h0; a1.h = h1; a0.t = a1.t = 1000.f;
 }
 
 /* ======================================================================================
@@ -567,38 +605,76 @@ __device__ __forceinline__ unsigned member_bits(const WarpCtx& w, uint32_t cl, c
   }
   return ~bits & ((1u << RT_CLUSTER) - 1u);
 }
-/* append the flagged members of one cluster to the sphere list */
-__device__ __forceinline__ void gather2(const WarpCtx& w, unsigned bits, uint32_t cl, uint32_t sub, int& cnt2,
-                                        bool& overflow) {
-  while (bits) {
-    const int b = 31 - __clz(bits);
-    bits &= ~(1u << b);
-    if (cnt2 < RT_LIST_MAX) {
-      w.list[cnt2 * RT_BLOCK + w.tid] =
-          (unsigned short)((sub << 14) | w.midx[cl * RT_CLUSTER + (uint32_t)(RT_CLUSTER - 1 - b)]);
-      ++cnt2;
-    } else {
-      overflow = true;
+
+/* The accelerated mode's three-stage rounds: cluster loop until a lane's (sub, cluster) list could
+ * overflow, member filter of the listed clusters, exact resolve of the surviving spheres (the sphere
+ * list is flushed whenever it fills up); repeat until the cluster loop is through. */
+template <int ND, int G, class Signs, class Members, class Resolve>
+__device__ __forceinline__ bool accel_rounds(const TraceParams& p, WarpCtx& w, uint32_t nPad, unsigned msk, Signs signs,
+                                             Members members, Resolve resolve) {
+  uint32_t base = 0;
+  bool overflow = false;
+  for (;;) {
+    int cnt = 0;
+    bool full = false;
+    for (; base < nPad; base += G) {
+      const unsigned comb = ~signs(base) & msk;
+      if (__any_sync(RT_FULL, cnt + __popc(comb) > (int)p.list1Max)) { full = true; break; }
+      if (comb) gather1<ND, G>(w, comb, base, cnt);
     }
+    RT_TICK(2);
+    const int maxc = __reduce_max_sync(RT_FULL, cnt);
+    /* members of the listed clusters -> sphere list -> exact tests.  A lane whose sphere list overflows
+     * (rare: > RT_LIST_MAX surviving spheres between two flushes of the cluster list) reports it and is
+     * answered by the exact test against every sphere */
+    int cnt2 = 0;
+#pragma unroll 1
+    for (int k = 0; k < maxc; ++k) {
+      if (k < cnt) {
+        const uint32_t e = w.list1[k * RT_BLOCK + w.tid];
+        const uint32_t cl = e & 0x3FFFu, sub = e >> 14;
+        unsigned bits = members(cl, sub);
+        while (bits) {
+          const int b = 31 - __clz(bits);
+          bits &= ~(1u << b);
+          if (cnt2 < RT_LIST_MAX) {
+            w.list[cnt2 * RT_BLOCK + w.tid] =
+                (unsigned short)((sub << 14) | w.midx[cl * RT_CLUSTER + (uint32_t)(RT_CLUSTER - 1 - b)]);
+            ++cnt2;
+          } else {
+            overflow = true;
+          }
+        }
+      }
+    }
+    const int maxc2 = __reduce_max_sync(RT_FULL, cnt2);
+#pragma unroll 1
+    for (int j = 0; j < maxc2; ++j)
+      if (j < cnt2 && !overflow) resolve((uint32_t)w.list[j * RT_BLOCK + w.tid]);
+    RT_TICK(3);
+    if (!full) break;
   }
+  return overflow;
 }
 
-template <bool USE_CONST>
-__device__ __forceinline__ void pass_trace_accel(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
-                                                 int s1, Counters& ctr) {
+template <class St>
+__device__ __forceinline__ void pass_trace_accel(const TraceParams& p, WarpCtx& w, const St& st, int s0, int s1,
+                                                 Counters& ctr, Answer& a0, Answer& a1) {
   constexpr int G = RT_GROUP_TA;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
   DirQ D0, D1;
   D0.ndx = D0.ndy = D0.ndz = D0.od = 0.f; D1 = D0;
   bool live0 = false, live1 = false, exact0 = false, exact1 = false;
   if (s0 >= 0) {
-    O0 = make_origin(slots[s0].qo);
-    live0 = make_dir(D0, slots[s0].qo, slots[s0].rayD);
+    const V3 o = st.ldv(s0, W_P), d = st.ldv(s0, W_RAYD);
+    O0 = make_origin(o);
+    live0 = make_dir_fast(D0, o, d);
     exact0 = live0 && (p.noFilter || !(origin_filterable(O0) && dir_filterable(D0)));
   }
   if (s1 >= 0) {
-    O1 = make_origin(slots[s1].qo);
-    live1 = make_dir(D1, slots[s1].qo, slots[s1].rayD);
+    const V3 o = st.ldv(s1, W_P), d = st.ldv(s1, W_RAYD);
+    O1 = make_origin(o);
+    live1 = make_dir_fast(D1, o, d);
     exact1 = live1 && (p.noFilter || !(origin_filterable(O1) && dir_filterable(D1)));
   }
   constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
@@ -607,320 +683,408 @@ __device__ __forceinline__ void pass_trace_accel(const TraceParams& p, const Con
   const Dir2 DD = pack_dir(D0, D1);
   float t0 = 1000.f, t1 = 1000.f;
   int h0 = -1, h1 = -1;
-  bool overflow = false;
   RT_TICK(1);
-  const uint32_t nPad = pin(p.noFilter ? 0u : w.nPad);
-  uint32_t base = 0;
-  for (;;) {
-    int cnt = 0;
-    bool full = false;
-    for (; base < nPad; base += G) {
-      unsigned k = 0;
+  const bool ovf = accel_rounds<2, G>(
+      p, w, pin(p.noFilter ? 0u : w.nPad), msk,
+      [&](uint32_t base) {
+        unsigned k = 0;
 #pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
-        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
-        const f32x2 b = bq2(DD, cx, cy, cz);
-        f32x2 ch = fma2(OO.px, cx, pk1(s.w));
-        ch = fma2(OO.py, cy, ch);
-        ch = fma2(OO.pz, cz, ch);
-        const f32x2 d = fma2(b, b, sub2(OO.nq, ch));
-        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
-        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
-      }
-      const unsigned comb = ~k & msk;
-      if (__any_sync(RT_FULL, cnt + __popc(comb) > (int)p.list1Max)) { full = true; break; }
-      if (comb) gather1<2, G>(w, comb, base, cnt);
-    }
-    RT_TICK(2);
-    /* members of the surviving clusters */
-    /* members of the surviving clusters */
-    int cnt2 = 0;
-    const int maxc = __reduce_max_sync(RT_FULL, cnt);
-#pragma unroll 1
-    for (int k = 0; k < maxc; ++k) {
-      if (k < cnt) {
-        const uint32_t e = w.list1[k * RT_BLOCK + w.tid];
-        const uint32_t cl = e & 0x3FFFu, sub = e >> 14;
-        OriginQ O = O0; DirQ D = D0;
-        if (sub) { O = O1; D = D1; }
-        gather2(w, member_bits<true>(w, cl, O, D), cl, sub, cnt2, overflow);
-      }
-    }
-    const int maxc2 = __reduce_max_sync(RT_FULL, cnt2);
-#pragma unroll 1
-    for (int k = 0; k < maxc2; ++k) {
-      if (k < cnt2 && !overflow) {
-        const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+        for (int j = 0; j < G; ++j) {
+          const float4 v = w.filt[base + j];
+          const f32x2 cx = pk1(v.x), cy = pk1(v.y), cz = pk1(v.z);
+          const f32x2 b = bq2(DD, cx, cy, cz);
+          f32x2 ch = fma2(OO.px, cx, pk1(v.w));
+          ch = fma2(OO.py, cy, ch);
+          ch = fma2(OO.pz, cz, ch);
+          const f32x2 d = fma2(b, b, sub2(OO.nq, ch));
+          k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+          k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
+        }
+        return k;
+      },
+      [&](uint32_t cl, uint32_t sub) { return sub ? member_bits<true>(w, cl, O1, D1) : member_bits<true>(w, cl, O0, D0); },
+      [&](uint32_t e) {
         const uint32_t i = e & 0x3FFFu, sub = e >> 14;
         if (i < p.sc.n) {
           ctr.exactTests++;
-          const Slot& q = slots[sub ? s1 : s0];
-          const float t = ray_sphere_t(p.sc.geo[i], q.qo, q.rayD);
+          const int sl = sub ? s1 : s0;
+          const float t = ray_sphere_t(p.sc.geo[i], st.ldv(sl, W_P), st.ldv(sl, W_RAYD));
           if (t > 0.f) {       /* raytracer.h:166-188: closest hit, the first index wins ties */
             if (sub) { if (t < t1 || (t == t1 && (int)i < h1)) { t1 = t; h1 = (int)i; } }
             else     { if (t < t0 || (t == t0 && (int)i < h0)) { t0 = t; h0 = (int)i; } }
           }
         }
-      }
-    }
-    RT_TICK(3);
-    if (!full) break;
-  }
-  if (overflow) { exact0 = live0; exact1 = live1; }
-  if (s0 >= 0) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
-  if (s1 >= 0) { slots[s1].minT = t1; slots[s1].hitIdx = h1; }
-  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
-  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+      });
+  if (ovf) { exact0 = live0; exact1 = live1; }
+  if (exact0) exact_trace(p.sc, st.ldv(s0, W_P), st.ldv(s0, W_RAYD), &t0, &h0, &ctr.exactTests);
+  if (exact1) exact_trace(p.sc, st.ldv(s1, W_P), st.ldv(s1, W_RAYD), &t1, &h1, &ctr.exactTests);
+  a0.t = t0; a0.h = h0; a1.t = t1; a1.h = h1;
 }
 
-template <bool USE_CONST, int ND>
-__device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
-                                                  Counters& ctr) {
-  constexpr int G = (ND == 4) ? RT_GROUP_S4A : RT_GROUP_S2;
+template <class St>
+__device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx& w, const St& st, int s0, bool asTrace,
+                                                  Counters& ctr, Answer& a0, ShadowRays& R) {
+  constexpr int ND = RT_SHADOW_BATCH;
+  constexpr int G = RT_GROUP_S4A;
   OriginQ O = make_origin(mk(0.f, 0.f, 0.f));
   DirQ D[ND];
   unsigned live = 0u, exact = 0u;
-  bool asTrace = false;
+  V3 org = mk(0.f, 0.f, 0.f);
+  V3 riderD = mk(0.f, 0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; }
+  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; R.gap[k] = 0.f; }
   if (s0 >= 0) {
-    asTrace = slots[s0].kind == K_TRACE;
-    ShadowGeo g;
-    V3 org;
-    if (asTrace) {
-      org = slots[s0].qo;
-      g.d[0] = slots[s0].rayD; g.gap[0] = 0.f;
-#pragma unroll
-      for (int k = 1; k < RT_SHADOW_BATCH; ++k) { g.d[k] = mk(0.f, 0.f, 0.f); g.gap[k] = 0.f; }
-    } else {
-      org = slots[s0].P;
-      shadow_geo(slots[s0], p.sc, g);
-    }
-#pragma unroll
-    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
-      w.geo[(4 * k + 0) * RT_BLOCK + w.tid] = g.d[k].x;
-      w.geo[(4 * k + 1) * RT_BLOCK + w.tid] = g.d[k].y;
-      w.geo[(4 * k + 2) * RT_BLOCK + w.tid] = g.d[k].z;
-      w.geo[(4 * k + 3) * RT_BLOCK + w.tid] = g.gap[k];
-    }
+    org = st.ldv(s0, W_P);
     O = make_origin(org);
     const bool ofil = origin_filterable(O);
-    const int nd = slots[s0].ndirs;
+    if (asTrace) {
+      riderD = st.ldv(s0, W_RAYD);
+      if (make_dir_fast(D[0], org, riderD)) {
+        live = 1u;
+        if (p.noFilter || !(ofil && dir_filterable(D[0]))) exact = 1u;
+      }
+    } else {
+      const uint32_t hdr = st.at(s0, W_HDR);
+      const int nd = (int)((hdr >> 2) & 7u), light = (int)(hdr >> 10);
 #pragma unroll
-    for (int k = 0; k < ND; ++k) {
-      if (k < nd && make_dir(D[k], org, g.d[k])) {
-        live |= 1u << k;
-        if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
+      for (int k = 0; k < ND; ++k) {
+        if (k < nd) {
+          const float4_ lp = p.sc.lpos[light + k];
+          const V3 dir = vsub(mk(lp.x, lp.y, lp.z), org);
+          R.gap[k] = vdot(dir, dir);
+          make_dir_unit(D[k], org, vunit(dir));
+          live |= 1u << k;
+          if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
+        }
       }
     }
   }
+  R.DP[0] = pack_dir(D[0], D[1]);
+  R.DP[1] = pack_dir(D[2], D[3]);
   unsigned msk = 0u;
 #pragma unroll
   for (int k = 0; k < ND; ++k) msk |= (((live & ~exact) >> k) & 1u) ? mask_of_sub<ND, G>(k) : 0u;
   msk = pin(msk);
-  Dir2 DP[ND / 2];
-#pragma unroll
-  for (int k = 0; k < ND / 2; ++k) DP[k] = pack_dir(D[2 * k], D[2 * k + 1]);
   const OriginQ OC = cluster_origin(O);
   unsigned blocked = 0u;
   float t0 = 1000.f;
   int h0 = -1;
-  bool overflow = false;
   RT_TICK(1);
-  const uint32_t nPad = pin(p.noFilter ? 0u : w.nPad);
-  uint32_t base = 0;
-  for (;;) {
-    int cnt = 0;
-    bool full = false;
-    for (; base < nPad; base += G) {
-      unsigned sk = 0u;
+  const bool ovf = accel_rounds<ND, G>(
+      p, w, pin(p.noFilter ? 0u : w.nPad), msk,
+      [&](uint32_t base) {
+        unsigned sk = 0u;
 #pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
-        const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
-        const f32x2 e = pk1(ex_sub(OC.nq, filter_ch(OC, s)));
+        for (int j = 0; j < G; ++j) {
+          const float4 v = w.filt[base + j];
+          float4_ s; s.x = v.x; s.y = v.y; s.z = v.z; s.w = v.w;
+          const f32x2 cx = pk1(s.x), cy = pk1(s.y), cz = pk1(s.z);
+          const f32x2 e = pk1(ex_sub(OC.nq, filter_ch(OC, s)));
 #pragma unroll
-        for (int k = 0; k < ND / 2; ++k) {
-          const f32x2 b = bq2(DP[k], cx, cy, cz);
-          const f32x2 d = fma2(b, b, e);
-          sk = __funnelshift_l(__float_as_uint(lo_of(d)), sk, 1);
-          sk = __funnelshift_l(__float_as_uint(hi_of(d)), sk, 1);
+          for (int k = 0; k < ND / 2; ++k) {
+            const f32x2 b = bq2(R.DP[k], cx, cy, cz);
+            const f32x2 d = fma2(b, b, e);
+            sk = __funnelshift_l(__float_as_uint(lo_of(d)), sk, 1);
+            sk = __funnelshift_l(__float_as_uint(hi_of(d)), sk, 1);
+          }
         }
-      }
-      const unsigned comb = ~sk & msk;
-      if (__any_sync(RT_FULL, cnt + __popc(comb) > (int)p.list1Max)) { full = true; break; }
-      if (comb) gather1<ND, G>(w, comb, base, cnt);
-    }
-    RT_TICK(2);
-    int cnt2 = 0;
-    const int maxc = __reduce_max_sync(RT_FULL, cnt);
-#pragma unroll 1
-    for (int k = 0; k < maxc; ++k) {
-      if (k < cnt) {
-        const uint32_t e = w.list1[k * RT_BLOCK + w.tid];
-        const uint32_t cl = e & 0x3FFFu, sub = e >> 14;
+        return sk;
+      },
+      [&](uint32_t cl, uint32_t sub) {
         DirQ Ds = D[0];
 #pragma unroll
         for (int j = 1; j < ND; ++j) if (sub == (uint32_t)j) Ds = D[j];
-        gather2(w, member_bits<true>(w, cl, O, Ds), cl, sub, cnt2, overflow);
-      }
-    }
-    const int maxc2 = __reduce_max_sync(RT_FULL, cnt2);
-#pragma unroll 1
-    for (int k = 0; k < maxc2; ++k) {
-      if (k < cnt2 && !overflow) {
-        const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+        return member_bits<true>(w, cl, O, Ds);
+      },
+      [&](uint32_t e) {
         const uint32_t i = e & 0x3FFFu, sub = e >> 14;
         if (i < p.sc.n && !((blocked >> sub) & 1u)) {
           ctr.exactTests++;
-          const V3 d = mk(w.geo[(4 * sub + 0) * RT_BLOCK + w.tid], w.geo[(4 * sub + 1) * RT_BLOCK + w.tid],
-                          w.geo[(4 * sub + 2) * RT_BLOCK + w.tid]);
-          const V3 org = asTrace ? slots[s0].qo : slots[s0].P;
+          const V3 d = asTrace ? riderD : shadow_dir(R, sub);
           const float t = ray_sphere_t(p.sc.geo[i], org, d);
           if (t > 0.f) {
             if (asTrace) {
               if (t < t0 || (t == t0 && (int)i < h0)) { t0 = t; h0 = (int)i; }
             } else if (t < 1000.f) {
               const V3 dist = vscale(t, d);
-              if (vdot(dist, dist) < w.geo[(4 * sub + 3) * RT_BLOCK + w.tid]) blocked |= 1u << sub;
+              const float gp = (sub & 2u) ? ((sub & 1u) ? R.gap[3] : R.gap[2]) : ((sub & 1u) ? R.gap[1] : R.gap[0]);
+              if (vdot(dist, dist) < gp) blocked |= 1u << sub;
             }
           }
         }
-      }
+      });
+  if (ovf) exact = live;
+  if (exact) {
+    if (asTrace) {
+      exact_trace(p.sc, org, riderD, &t0, &h0, &ctr.exactTests);
+    } else {
+#pragma unroll
+      for (int k = 0; k < ND; ++k)
+        if ((exact >> k) & 1u) {
+          blocked &= ~(1u << k);
+          if (exact_shadow(p.sc, org, shadow_dir(R, (uint32_t)k), R.gap[k], &ctr.exactTests)) blocked |= 1u << k;
+        }
     }
-    RT_TICK(3);
-    if (!full) break;
   }
-  if (overflow) exact = live;
-  if (s0 >= 0) {
-    if (asTrace) { slots[s0].minT = t0; slots[s0].hitIdx = h0; }
-    else slots[s0].blocked = blocked;
-  }
-  if (exact) ctr.exactTests += exact_all(p.sc, &slots[s0], exact);
+  a0.t = t0; a0.h = h0; a0.blocked = blocked;
 }
 
-template <bool USE_CONST>
-__device__ __forceinline__ void pass_contain_accel(const TraceParams& p, const ConstRecords& cr, WarpCtx& w, Slot* slots, int s0,
-                                                   int s1, Counters& ctr) {
+template <class St>
+__device__ __forceinline__ void pass_contain_accel(const TraceParams& p, WarpCtx& w, const St& st, int s0, int s1,
+                                                   Counters& ctr, Answer& a0, Answer& a1) {
   constexpr int G = RT_GROUP_CA;
   OriginQ O0 = make_origin(mk(0.f, 0.f, 0.f)), O1 = O0;
+  V3 q0 = mk(0.f, 0.f, 0.f), q1 = q0;
   bool exact0 = false, exact1 = false;
-  if (s0 >= 0) { O0 = make_origin(slots[s0].qo); exact0 = p.noFilter || !origin_filterable(O0); }
-  if (s1 >= 0) { O1 = make_origin(slots[s1].qo); exact1 = p.noFilter || !origin_filterable(O1); }
+  if (s0 >= 0) { q0 = vadd(vscale(0.01f, st.ldv(s0, W_RAYD)), st.ldv(s0, W_P)); O0 = make_origin(q0); exact0 = p.noFilter || !origin_filterable(O0); }
+  if (s1 >= 0) { q1 = vadd(vscale(0.01f, st.ldv(s1, W_RAYD)), st.ldv(s1, W_P)); O1 = make_origin(q1); exact1 = p.noFilter || !origin_filterable(O1); }
   constexpr unsigned m0 = mask_of_sub<2, G>(0), m1 = mask_of_sub<2, G>(1);
   const unsigned msk = pin(((s0 >= 0 && !exact0) ? m0 : 0u) | ((s1 >= 0 && !exact1) ? m1 : 0u));
   const Origin2 OO = pack_origin(cluster_origin(O0), cluster_origin(O1));
   int h0 = -1, h1 = -1;
-  bool overflow = false;
-  RT_TICK(1);
-  const uint32_t nPad = pin(p.noFilter ? 0u : w.nPad);
-  uint32_t base = 0;
   DirQ none;
   none.ndx = none.ndy = none.ndz = none.od = 0.f;
-  for (;;) {
-    int cnt = 0;
-    bool full = false;
-    for (; base < nPad; base += G) {
-      unsigned k = 0;
+  RT_TICK(1);
+  const bool ovf = accel_rounds<2, G>(
+      p, w, pin(p.noFilter ? 0u : w.nPad), msk,
+      [&](uint32_t base) {
+        unsigned k = 0;
 #pragma unroll
-      for (int j = 0; j < G; ++j) {
-        const float4_ s = load_filt<USE_CONST>(w, cr, base + j);
-        f32x2 ch = fma2(OO.px, pk1(s.x), pk1(s.w));
-        ch = fma2(OO.py, pk1(s.y), ch);
-        ch = fma2(OO.pz, pk1(s.z), ch);
-        const f32x2 d = sub2(OO.nq, ch);
-        k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
-        k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
-      }
-      const unsigned comb = ~k & msk;
-      if (__any_sync(RT_FULL, cnt + __popc(comb) > (int)p.list1Max)) { full = true; break; }
-      if (comb) gather1<2, G>(w, comb, base, cnt);
-    }
-    RT_TICK(2);
-    int cnt2 = 0;
-    const int maxc = __reduce_max_sync(RT_FULL, cnt);
-#pragma unroll 1
-    for (int k = 0; k < maxc; ++k) {
-      if (k < cnt) {
-        const uint32_t e = w.list1[k * RT_BLOCK + w.tid];
-        const uint32_t cl = e & 0x3FFFu, sub = e >> 14;
-        OriginQ O = O0;
-        if (sub) O = O1;
-        gather2(w, member_bits<false>(w, cl, O, none), cl, sub, cnt2, overflow);
-      }
-    }
-    const int maxc2 = __reduce_max_sync(RT_FULL, cnt2);
-#pragma unroll 1
-    for (int k = 0; k < maxc2; ++k) {
-      if (k < cnt2 && !overflow) {
-        const uint32_t e = w.list[k * RT_BLOCK + w.tid];
+        for (int j = 0; j < G; ++j) {
+          const float4 v = w.filt[base + j];
+          f32x2 ch = fma2(OO.px, pk1(v.x), pk1(v.w));
+          ch = fma2(OO.py, pk1(v.y), ch);
+          ch = fma2(OO.pz, pk1(v.z), ch);
+          const f32x2 d = sub2(OO.nq, ch);
+          k = __funnelshift_l(__float_as_uint(lo_of(d)), k, 1);
+          k = __funnelshift_l(__float_as_uint(hi_of(d)), k, 1);
+        }
+        return k;
+      },
+      [&](uint32_t cl, uint32_t sub) { return member_bits<false>(w, cl, sub ? O1 : O0, none); },
+      [&](uint32_t e) {
         const uint32_t i = e & 0x3FFFu, sub = e >> 14;
         if (i < p.sc.n) {
           ctr.exactTests++;
-          const bool in = contains_exact(p.sc.geo[i], slots[sub ? s1 : s0].qo);
+          const bool in = contains_exact(p.sc.geo[i], sub ? q1 : q0);
           if (in) {            /* raytracer.h:264: the first container in index order wins */
             if (sub) { if (h1 < 0 || (int)i < h1) h1 = (int)i; }
             else     { if (h0 < 0 || (int)i < h0) h0 = (int)i; }
           }
         }
-      }
-    }
-    RT_TICK(3);
-    if (!full) break;
-  }
-  if (overflow) { exact0 = s0 >= 0; exact1 = s1 >= 0; }
-  if (s0 >= 0) slots[s0].hitIdx = h0;
-  if (s1 >= 0) slots[s1].hitIdx = h1;
-  if (exact0) ctr.exactTests += exact_all(p.sc, &slots[s0], 1u);
-  if (exact1) ctr.exactTests += exact_all(p.sc, &slots[s1], 1u);
+      });
+  if (ovf) { exact0 = s0 >= 0; exact1 = s1 >= 0; }
+  if (exact0) h0 = exact_contain(p.sc, q0, &ctr.exactTests);
+  if (exact1) h1 = exact_contain(p.sc, q1, &ctr.exactTests);
+  a0.h = h0; a1.h = h1; a0.t = a1.t = 1000.f;
 }
 
-/* Pull the state words of a slot that is about to be served into L1 while the sphere loop
- * runs: the per-lane slots live in local memory (one 128-byte line per word per warp), far
- * more than L1 holds across all resident warps, so without this the O(1) code after the loop
- * waits on L2 for every field it touches. */
-__device__ __forceinline__ void prefetch_slot(const Slot& s) {
-  const float* w = reinterpret_cast<const float*>(&s);
-  constexpr int WORDS = (int)((sizeof(Slot) - sizeof(Frame) * RT_MAX_STACK) / sizeof(float));
-#pragma unroll 1
-  for (int i = 0; i < WORDS; ++i)
-    asm volatile("{ .reg .u64 la; cvta.to.local.u64 la, %0; prefetch.local.L1 [la]; }" ::"l"(w + i));
-}
-
-/* Advance one served slot; store the pixel when it completes.  The slot record is copied
- * into registers first (one batch of independent local loads instead of a dependent
- * load/store chain through L2) and written back once.  Returns the slot's new
+/* Advance the served slot of every lane (sv < 0: none); store the pixel when a sample completes.  The
+ * record is read into registers, taken through the state machine of rt_core.cuh and written back once,
+ * AFTER the warp has reconverged (__syncwarp keeps the compiler from copying the write-back into every
+ * divergent tail of the machine).  Must be called by all 32 lanes.  Returns the slot's new
  * (kind | ndirs << 4) tag for the lane's register-resident census. */
-__device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, Slot* slot, Frame* stack, Counters& ctr,
-                                                 float& laneMax, const ShadowGeo* sg) {
-  Slot s = *slot;
-  if (advance(s, stack, ctr, p.sc, p.cam, sg)) {
+template <class St>
+__device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, const St& st, int sv, Frame* stack, Counters& ctr,
+                                                 float& laneMax, const ShadowGeo* sg, const Answer& ans) {
+  Slot s;
+  bool done = false;
+#if RT_ADV_CONVERGENT
+  if (sv >= 0) {
+    load_slot(st, sv, s);
+    s.minT = ans.t; s.hitIdx = ans.h; s.blocked = ans.blocked;
+    done = advance(s, stack, ctr, p.sc, p.cam, sg);
+  }
+  __syncwarp();
+  if (sv < 0) return 0u;
+#else
+  if (sv < 0) return 0u;
+  load_slot(st, sv, s);
+  s.minT = ans.t; s.hitIdx = ans.h; s.blocked = ans.blocked;
+  done = advance(s, stack, ctr, p.sc, p.cam, sg);
+#endif
+  if (done) {
     const V3 v = sample_value(s, p.cam);
     if (p.spp == 1u) {
       /* one sample per pixel: the pixel is 0 + sample (main.cpp:420,446) */
       const V3 a = vadd(mk(0.f, 0.f, 0.f), v);
-      p.fb[s.pixel] = make_float4(a.x, a.y, a.z, 1.f);
+      __stcs(&p.fb[s.pixel], make_float4(a.x, a.y, a.z, 1.f));      /* streaming: keeps L2 for the sample state */
       if (a.x > laneMax) laneMax = a.x;   /* algebra.h:74-82, NaN skipped */
       if (a.y > laneMax) laneMax = a.y;
       if (a.z > laneMax) laneMax = a.z;
     } else {
-      p.samples[s.pixel] = make_float4(v.x, v.y, v.z, 1.f);
+      __stcs(&p.samples[s.pixel], make_float4(v.x, v.y, v.z, 1.f));
     }
-    s.pixel = RT_NO_PIXEL;
     s.kind = K_NULL;
     s.ndirs = 0;
+    st.at(sv, W_PIXEL) = RT_NO_PIXEL;
+    st.at(sv, W_HDR) = 0u;
+  } else {
+    store_slot(st, sv, s);
   }
-  *slot = s;
   return (uint32_t)s.kind | ((uint32_t)s.ndirs << 4);
 }
 
-template <bool USE_CONST, int NSLOTS, bool ACCEL>
+/* Drain balancing.  Once the tile queue is dry a lane's slots are no longer refilled, and a pass costs the
+ * same however few lanes it serves: the warp would run until its BUSIEST lane has worked off its slots
+ * one or two queries at a time.  Instead, whenever two lanes' live-slot counts differ by two or more, the
+ * fullest lanes hand one slot each (21-word record + its suspended frames + its census byte) to the
+ * emptiest lanes through shuffles, so the warp's passes stay full until it holds fewer queries than lanes.
+ * Samples are independent (main.cpp:439) and carry their result index, so any lane may finish them. */
+template <int NSLOTS, class St>
+__device__ __forceinline__ void rebalance(const St& st, Frame* stacks, uint32_t& tags, uint32_t lane, uint32_t& migrated) {
+#pragma unroll 1
+  for (int round = 0; round < NSLOTS; ++round) {
+    int live = 0, ks = -1, kr = -1;
+#pragma unroll
+    for (int k = 0; k < NSLOTS; ++k) {
+      const bool lv = ((tags >> (8 * k)) & 0xFu) != (uint32_t)K_NULL;
+      live += lv ? 1 : 0;
+      if (lv) ks = k; else if (kr < 0) kr = k;      /* a donor gives its last live slot, a receiver fills its first free one */
+    }
+    const int mx = __reduce_max_sync(RT_FULL, live), mn = __reduce_min_sync(RT_FULL, live);
+    if (mx - mn < 2) return;
+    const unsigned dmask = __ballot_sync(RT_FULL, live == mx), rmask = __ballot_sync(RT_FULL, live == mn);
+    const int npairs = min(__popc(dmask), __popc(rmask));
+    const unsigned lt = (1u << lane) - 1u;
+    const int rankD = __popc(dmask & lt), rankR = __popc(rmask & lt);
+    const bool isD = (live == mx) && rankD < npairs, isR = (live == mn) && rankR < npairs;
+    int partner = (int)lane;
+    if (isR) partner = (int)__fns(dmask, 0, rankR + 1);      /* the rankR-th donor */
+    if (isD) partner = (int)__fns(rmask, 0, rankD + 1);
+    const int nfD = isD ? (int)((st.at(ks, W_HDR) >> 5) & 31u) : 0;      /* frames in use = top + 1 */
+#pragma unroll 1
+    for (int wd = 0; wd < RT_SLOT_WORDS; ++wd) {
+      uint32_t v = isD ? st.at(ks, wd) : 0u;
+      v = __shfl_sync(RT_FULL, v, partner);
+      if (isR) st.at(kr, wd) = v;
+    }
+    const int nf = __shfl_sync(RT_FULL, nfD, partner);
+    const int nfMax = __reduce_max_sync(RT_FULL, nfD);
+    uint32_t* fw = reinterpret_cast<uint32_t*>(stacks);
+    constexpr int FW = (int)(sizeof(Frame) / sizeof(uint32_t));
+#pragma unroll 1
+    for (int f = 0; f < nfMax; ++f) {
+#pragma unroll 1
+      for (int wd = 0; wd < FW; ++wd) {
+        uint32_t v = (isD && f < nfD) ? fw[(ks * RT_MAX_STACK + f) * FW + wd] : 0u;
+        v = __shfl_sync(RT_FULL, v, partner);
+        if (isR && f < nf) fw[(kr * RT_MAX_STACK + f) * FW + wd] = v;
+      }
+    }
+    const uint32_t tgD = isD ? ((tags >> (8 * ks)) & 0xFFu) : 0u;
+    const uint32_t tg = __shfl_sync(RT_FULL, tgD, partner);
+    if (isR) { tags = (tags & ~(0xFFu << (8 * kr))) | (tg << (8 * kr)); ++migrated; }
+    if (isD) {
+      tags &= ~(0xFFu << (8 * ks));
+      st.at(ks, W_PIXEL) = RT_NO_PIXEL;
+      st.at(ks, W_HDR) = 0u;
+    }
+  }
+}
+
+/* Sparse rounds (the end of a warp's drain).  A sample is a chain of up to several hundred dependent
+ * queries (a depth-8 tree has up to 255 calls of three queries each), and a normal pass costs the full
+ * sphere loop however few queries it serves: the last samples of a launch would keep an almost empty SM
+ * busy for milliseconds.  Once a warp holds only a handful of queries it serves them ONE AT A TIME with
+ * the spheres spread over the lanes: lane l filters spheres l, l+32, ..., puts its own candidates through
+ * the reference's exact expressions, and a warp reduction picks the answer (closest hit with the first
+ * index winning ties, occlusion bits, first container).  Same arithmetic per (query, sphere) pair as the
+ * passes, so the answers — and the frame — are bit-identical. */
+template <bool USE_CONST, bool ACCEL, class St>
+__device__ __forceinline__ void sparse_query(const TraceParams& p, const ConstRecords& cr, const WarpCtx& w, const St& st,
+                                             int owner, int ks, uint32_t lane, Counters& ctr, Answer& ans, ShadowGeo& sg) {
+  /* the per-sphere filter records: staged copy, or (accelerated mode: only the cluster form is staged) global memory */
+  auto rec = [&](uint32_t i) { return ACCEL ? p.sc.filt[i] : load_filt<USE_CONST>(w, cr, i); };
+  /* the owner's record header and geometry, broadcast */
+  const bool mine = (int)lane == owner;
+  const uint32_t hdr = __shfl_sync(RT_FULL, mine ? st.at(ks, W_HDR) : 0u, owner);
+  const int kind = (int)(hdr & 3u), nd = (int)((hdr >> 2) & 7u), light = (int)(hdr >> 10);
+  V3 P = mine ? st.ldv(ks, W_P) : mk(0.f, 0.f, 0.f), d = mine ? st.ldv(ks, W_RAYD) : mk(0.f, 0.f, 0.f);
+  P.x = __shfl_sync(RT_FULL, P.x, owner); P.y = __shfl_sync(RT_FULL, P.y, owner); P.z = __shfl_sync(RT_FULL, P.z, owner);
+  d.x = __shfl_sync(RT_FULL, d.x, owner); d.y = __shfl_sync(RT_FULL, d.y, owner); d.z = __shfl_sync(RT_FULL, d.z, owner);
+  const uint32_t n = p.sc.n, nPad = p.sc.nPad;
+  ans.t = 1000.f; ans.h = -1; ans.blocked = 0u;
+  if (kind == K_TRACE) {
+    const OriginQ O = make_origin(P);
+    DirQ D;
+    if (make_dir_fast(D, P, d)) {                       /* zero direction: certain miss, no loop */
+      const bool exact = p.noFilter || !(origin_filterable(O) && dir_filterable(D));
+      float bt = 1000.f; uint32_t bi = 0x3FFFu;
+      for (uint32_t i = lane; i < nPad; i += 32u) {
+        bool cand = exact;
+        if (!exact) { const float4_ f = rec(i); cand = !(filter_ray(O, D, filter_ch(O, f), f) < 0.f); }
+        if (cand && i < n) {
+          ctr.exactTests++;
+          const float t = ray_sphere_t(p.sc.geo[i], P, d);
+          if (t > 0.f && t < bt) { bt = t; bi = i; }      /* increasing i per lane: strict < keeps the first index */
+        }
+      }
+      /* warp minimum of (t, index): positive floats order like their bit patterns */
+      unsigned long long key = ((unsigned long long)__float_as_uint(bt) << 32) | bi;
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(RT_FULL, key, o); key = k2 < key ? k2 : key; }
+      const float t = __uint_as_float((unsigned)(key >> 32));
+      if (t < 1000.f) { ans.t = t; ans.h = (int)(unsigned)(key & 0xFFFFFFFFu); }
+    }
+  } else if (kind == K_SHADOW) {
+    const OriginQ O = make_origin(P);
+    const bool ofil = origin_filterable(O);
+    DirQ D[RT_SHADOW_BATCH];
+    unsigned exact = 0u, blocked = 0u;
+#pragma unroll
+    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+      sg.d[k] = mk(0.f, 0.f, 0.f); sg.gap[k] = 0.f;
+      D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f;
+      if (k < nd) {
+        const float4_ lp = p.sc.lpos[light + k];
+        const V3 dir = vsub(mk(lp.x, lp.y, lp.z), P);       /* raytracer.h:279-286 */
+        sg.gap[k] = vdot(dir, dir);
+        sg.d[k] = vunit_i(dir);
+        make_dir_unit(D[k], P, sg.d[k]);
+        if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
+      }
+    }
+    for (uint32_t i = lane; i < nPad; i += 32u) {
+      const float4_ f = rec(i);
+      const float ch = filter_ch(O, f);
+#pragma unroll
+      for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
+        if (k < nd && !((blocked >> k) & 1u) && i < n) {
+          const bool cand = ((exact >> k) & 1u) || !(filter_ray(O, D[k], ch, f) < 0.f);
+          if (cand) {
+            ctr.exactTests++;
+            if (resolve_shadow(P, sg.d[k], sg.gap[k], p.sc.geo[i])) blocked |= 1u << k;
+          }
+        }
+      }
+    }
+    ans.blocked = __reduce_or_sync(RT_FULL, blocked);
+  } else {   /* K_CONTAIN: the probe point of raytracer.h:688-692 */
+    const V3 q = vadd(vscale(0.01f, d), P);
+    const OriginQ O = make_origin(q);
+    const bool exact = p.noFilter || !origin_filterable(O);
+    unsigned first = 0xFFFFFFFFu;
+    for (uint32_t i = lane; i < nPad && first == 0xFFFFFFFFu; i += 32u) {
+      bool cand = exact;
+      if (!exact) { const float4_ f = rec(i); cand = !(filter_point(O, filter_ch(O, f)) < 0.f); }
+      if (cand && i < n) {
+        ctr.exactTests++;
+        if (contains_exact(p.sc.geo[i], q)) first = i;     /* increasing i per lane: this lane's first container */
+      }
+    }
+    first = __reduce_min_sync(RT_FULL, first);
+    ans.h = (first == 0xFFFFFFFFu) ? -1 : (int)first;
+  }
+}
+
+template <bool USE_CONST, int NSLOTS, bool ACCEL, bool SMEM_SLOTS>
 __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstRecords& cr) {
   static_assert(!(ACCEL && USE_CONST), "the accelerated mode stages its records in shared memory");
+  static_assert(NSLOTS >= 2 && NSLOTS <= 4, "the census register holds four slots");
   extern __shared__ __align__(128) unsigned char smem_raw[];
-  /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists][shadow-ray scratch];
-   * accelerated mode: [mbarrier][cluster records | member records | member indices][list1][list][scratch] */
+  /* layout: [mbarrier 16 B][filter records nPad*16 B (shared staging only)][lists][slot records (SMEM_SLOTS)];
+   * accelerated mode: [mbarrier][cluster records | member records | member indices][list1][list] */
   uint64_t* bar = reinterpret_cast<uint64_t*>(smem_raw);
   float4* sFilt = reinterpret_cast<float4*>(smem_raw + 16);
   const uint32_t filtBytes = USE_CONST ? 0u : ACCEL ? p.sc.ncPad * (16u + RT_CLUSTER * 18u) : p.sc.nPad * 16u;
@@ -952,7 +1116,6 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   const uint32_t list1Bytes = ACCEL ? p.list1Max * RT_BLOCK * (uint32_t)sizeof(unsigned short) : 0u;
   w.list1 = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes);
   w.list = reinterpret_cast<unsigned short*>(smem_raw + 16 + filtBytes + list1Bytes);
-  w.geo = reinterpret_cast<float*>(smem_raw + 16 + filtBytes + list1Bytes + RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short));
   w.tid = tid;
   w.nPad = ACCEL ? p.sc.ncPad : p.sc.nPad;
 #ifdef RT_PHASE_TIMING
@@ -960,16 +1123,21 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   for (int i = 0; i < 6; ++i) w.phase[i] = 0;
 #endif
 
-  Slot slots[NSLOTS];
+  uint32_t localSlots[SMEM_SLOTS ? 1 : NSLOTS * RT_SLOT_WORDS];
+  SlotStore<SMEM_SLOTS> st;
+  st.base = SMEM_SLOTS ? reinterpret_cast<uint32_t*>(smem_raw + 16 + filtBytes + list1Bytes +
+                                                     RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)) + tid
+                       : localSlots;
   Frame stacks[NSLOTS * RT_MAX_STACK];
 #pragma unroll 1
-  for (int k = 0; k < NSLOTS; ++k) { slots[k].kind = K_NULL; slots[k].pixel = RT_NO_PIXEL; slots[k].ndirs = 0; }
+  for (int k = 0; k < NSLOTS; ++k) { st.at(k, W_PIXEL) = RT_NO_PIXEL; st.at(k, W_HDR) = 0u; }
   uint32_t tags = 0u;   /* census kept in a register: byte k = kind | ndirs << 4 of slot k */
   Counters ctr;
   ctr.rays = ctr.shadow = ctr.containQ = ctr.containT = ctr.exactTests = ctr.samples = ctr.nullRays = 0;
   float laneMax = 0.f;
-  uint32_t passT = 0, passS2 = 0, passS4 = 0, passC = 0;   /* passes by kind (warp-uniform) */
+  uint32_t passT = 0, passS4 = 0, passC = 0;                /* passes by kind (warp-uniform) */
   uint32_t servedT = 0, servedS = 0, servedC = 0;            /* sub-queries of this lane served */
+  uint32_t migrated = 0;                                     /* slots this lane received from busier lanes */
 
   uint32_t wbase = 0, wend = 0;          /* warp-uniform slice of the tile queue */
   bool queueDry = false;
@@ -1002,7 +1170,11 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
           uint32_t gx, gy, dst;
           int si, sj;
           if (work_to_task(p, wbase + rank, gx, gy, dst, si, sj)) {
-            start_task(slots[k], ctr, p.cam, gx, gy, dst, si, sj);
+            Slot s;
+            s.obj = 0; s.light = 0;
+            s.P = s.Nrm = s.lit = mk(0.f, 0.f, 0.f);
+            start_task(s, ctr, p.cam, gx, gy, dst, si, sj);
+            store_slot(st, k, s);
             need = false;
             tags = (tags & ~(0xFFu << (8 * k))) | (((uint32_t)K_TRACE | (1u << 4)) << (8 * k));
           }
@@ -1011,6 +1183,8 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
         wbase += (cnt < avail) ? cnt : avail;
       }
     }
+
+    if (queueDry && p.rebalance) rebalance<NSLOTS>(st, stacks, tags, lane, migrated);
 
     /* ---- vote ---- */
     int t0 = -1, t1 = -1, s0 = -1, c0 = -1, c1 = -1, nd = 0;
@@ -1025,65 +1199,83 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
     /* a shadow pass also takes one trace ray from lanes that have no shadow batch waiting */
     const int sOrT = (s0 >= 0) ? s0 : t0;
     const int ndS = (s0 >= 0) ? nd : (t0 >= 0 ? 1 : 0);
-    const int ndMax = __reduce_max_sync(RT_FULL, nd);
     const unsigned nT = __reduce_add_sync(RT_FULL, (unsigned)((t0 >= 0) + (t1 >= 0)));
     const unsigned nS = __reduce_add_sync(RT_FULL, (unsigned)ndS);
     const unsigned nC = __reduce_add_sync(RT_FULL, (unsigned)((c0 >= 0) + (c1 >= 0)));
+    const int ndMax = __reduce_max_sync(RT_FULL, nd);
     if ((nT | nS | nC) == 0u) {
       if (queueDry) break;
       continue;
     }
+    /* the last few queries of this warp are served one at a time, lane-parallel over the spheres */
+    if (queueDry && p.sparseBelow && nT + nC + __popc(__ballot_sync(RT_FULL, s0 >= 0)) <= p.sparseBelow) break;
     /* serve the kind that fills the largest share of its pass: capacity 64 sub-queries for
-     * trace / contain passes, 32 x (2 or 4) for a shadow pass */
+     * trace / contain passes, 32 x (2 or 4) for a shadow pass (scenes with <= 2 lights fill half of it) */
     const unsigned capS = (ndMax <= 2) ? 64u : 128u;
-    int sv0, sv1;
     const bool anyS = ndMax > 0;
     const int mode = (anyS && nS * 64u >= nT * capS && nS * 64u >= nC * capS) ? K_SHADOW
                      : (nT >= nC) ? K_TRACE : K_CONTAIN;
-    sv0 = (mode == K_SHADOW) ? sOrT : (mode == K_TRACE) ? t0 : c0;
-    sv1 = (mode == K_SHADOW) ? -1 : (mode == K_TRACE) ? t1 : c1;
-    if (p.prefetch) {
-      if (sv0 >= 0) prefetch_slot(slots[sv0]);
-      if (sv1 >= 0) prefetch_slot(slots[sv1]);
-    }
+    const int sv0 = (mode == K_SHADOW) ? sOrT : (mode == K_TRACE) ? t0 : c0;
+    const int sv1 = (mode == K_SHADOW) ? -1 : (mode == K_TRACE) ? t1 : c1;
+    Answer a0, a1;
+    a0.t = a1.t = 1000.f; a0.h = a1.h = -1; a0.blocked = a1.blocked = 0u;
+    ShadowGeo sg;
     if (mode == K_SHADOW) {
-      if (ndMax <= 2 && !(ACCEL && RT_ACCEL_ONE_SHADOW)) {
-        if (ACCEL) pass_shadow_accel<USE_CONST, 2>(p, cr, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 2>(p, cr, w, slots, sv0, ctr);
-        passS2++;
-      } else {
-        if (ACCEL) pass_shadow_accel<USE_CONST, 4>(p, cr, w, slots, sv0, ctr); else pass_shadow<USE_CONST, 4>(p, cr, w, slots, sv0, ctr);
-        passS4++;
-      }
+      ShadowRays R;
+      const bool asTrace = (s0 < 0);
+      if (ACCEL) pass_shadow_accel(p, w, st, sv0, asTrace, ctr, a0, R);
+      else pass_shadow<USE_CONST>(p, cr, w, st, sv0, asTrace, ctr, a0, R);
+      passS4++;
       if (s0 >= 0) servedS += (unsigned)nd; else servedT += (unsigned)ndS;
+      /* the rays of the batch just served, as the state machine reads them */
+#pragma unroll
+      for (int k = 0; k < RT_SHADOW_BATCH; ++k) { sg.d[k] = shadow_dir(R, (uint32_t)k); sg.gap[k] = R.gap[k]; }
     } else if (mode == K_TRACE) {
-      if (ACCEL) pass_trace_accel<USE_CONST>(p, cr, w, slots, t0, t1, ctr); else pass_trace<USE_CONST>(p, cr, w, slots, t0, t1, ctr);
+      if (ACCEL) pass_trace_accel(p, w, st, t0, t1, ctr, a0, a1);
+      else pass_trace<USE_CONST>(p, cr, w, st, t0, t1, ctr, a0, a1);
       passT++; servedT += (unsigned)((t0 >= 0) + (t1 >= 0));
     } else {
-      if (ACCEL) pass_contain_accel<USE_CONST>(p, cr, w, slots, c0, c1, ctr); else pass_contain<USE_CONST>(p, cr, w, slots, c0, c1, ctr);
+      if (ACCEL) pass_contain_accel(p, w, st, c0, c1, ctr, a0, a1);
+      else pass_contain<USE_CONST>(p, cr, w, st, c0, c1, ctr, a0, a1);
       passC++; servedC += (unsigned)((c0 >= 0) + (c1 >= 0));
     }
-    RT_TICK(3);
     /* ---- advance the served slots (one code instance, same kind across the warp) ---- */
-    ShadowGeo sg;
-    if (mode == K_SHADOW && sv0 >= 0) {       /* the rays of the batch just served */
-#pragma unroll
-      for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
-        sg.d[k] = mk(w.geo[(4 * k + 0) * RT_BLOCK + tid], w.geo[(4 * k + 1) * RT_BLOCK + tid],
-                     w.geo[(4 * k + 2) * RT_BLOCK + tid]);
-        sg.gap[k] = w.geo[(4 * k + 3) * RT_BLOCK + tid];
-      }
-    }
 #pragma unroll 1
     for (int r = 0; r < 2; ++r) {
       const int sv = r ? sv1 : sv0;
-      if (sv >= 0) {
-        const uint32_t tg = advance_slot(p, &slots[sv], &stacks[sv * RT_MAX_STACK], ctr, laneMax, &sg);
-        tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
-      }
+      if (!__any_sync(RT_FULL, sv >= 0)) continue;
+      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * RT_MAX_STACK], ctr, laneMax, &sg, r ? a1 : a0);
+      if (sv >= 0) tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
     }
     RT_TICK(4);
   }
 
+  /* ---- sparse drain: whatever is still pending in this warp, one query at a time ---- */
+  uint32_t sparseQ = 0;
+  {
+    for (;;) {
+      int ks = -1;
+#pragma unroll
+      for (int k = NSLOTS - 1; k >= 0; --k)
+        if (((tags >> (8 * k)) & 0xFu) != (uint32_t)K_NULL) ks = k;
+      const unsigned m = __ballot_sync(RT_FULL, ks >= 0);
+      if (m == 0u) break;
+      const int owner = __ffs((int)m) - 1;
+      const int oks = __shfl_sync(RT_FULL, ks, owner);
+      Answer a;
+      ShadowGeo sg;
+      sparse_query<USE_CONST, ACCEL>(p, cr, w, st, owner, (int)lane == owner ? ks : oks, lane, ctr, a, sg);
+      const int sv = ((int)lane == owner) ? ks : -1;
+      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * RT_MAX_STACK], ctr, laneMax, &sg, a);
+      if (sv >= 0) {
+        const uint32_t old = (tags >> (8 * sv)) & 0xFFu;
+        const uint32_t subs = ((old & 0xFu) == (uint32_t)K_SHADOW) ? (old >> 4) : 1u;
+        if ((old & 0xFu) == (uint32_t)K_TRACE) servedT += subs; else if ((old & 0xFu) == (uint32_t)K_SHADOW) servedS += subs; else servedC += subs;
+        sparseQ += subs;
+        tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
+      }
+    }
+  }
 #ifdef RT_PHASE_TIMING
   if (lane == 0)
   {
@@ -1095,37 +1287,40 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   /* ---- per-warp reductions ---- */
   unsigned mb = __float_as_uint(laneMax);   /* laneMax >= 0: uint order == float order */
   mb = __reduce_max_sync(RT_FULL, mb);
-  unsigned long long v[10];
+  unsigned long long v[12];
   v[0] = ctr.rays; v[1] = ctr.shadow; v[2] = ctr.containQ; v[3] = ctr.containT;
   v[4] = ctr.exactTests; v[5] = ctr.samples; v[6] = ctr.nullRays;
-  v[7] = servedT; v[8] = servedS; v[9] = servedC;
+  v[7] = servedT; v[8] = servedS; v[9] = servedC; v[10] = sparseQ; v[11] = migrated;
 #pragma unroll
-  for (int i = 0; i < 10; ++i)
+  for (int i = 0; i < 12; ++i)
     for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(RT_FULL, v[i], o);
   if (lane == 0) {
     if (mb) atomicMax(p.maxBits, mb);
 #pragma unroll
     for (int i = 0; i < 10; ++i) atomicAdd(&p.counters[i], v[i]);
-    /* sub-query capacity offered by this warp's passes (32 lanes x 2 / ND / 2 per pass) */
-    atomicAdd(&p.counters[10], 64ull * passT + 64ull * passS2 + 128ull * passS4 + 64ull * passC);
-    atomicAdd(&p.counters[11], 1ull * passT + 1ull * passS2 + 1ull * passS4 + 1ull * passC);
+    atomicAdd(&p.counters[22], v[10]);
+    atomicAdd(&p.counters[23], v[11]);
+    /* sub-query capacity offered by this warp's passes (32 lanes x 2, or x 4 for a shadow pass; a sparse round
+     * offers exactly the query it serves) */
+    atomicAdd(&p.counters[10], 64ull * passT + 128ull * passS4 + 64ull * passC + v[10]);
+    atomicAdd(&p.counters[11], 1ull * passT + 1ull * passS4 + 1ull * passC);
     atomicAdd(&p.counters[12], (unsigned long long)passT);
-    atomicAdd(&p.counters[13], (unsigned long long)passS2);
     atomicAdd(&p.counters[14], (unsigned long long)passS4);
     atomicAdd(&p.counters[15], (unsigned long long)passC);
   }
 }
 
-/* The two entry points: records staged in shared memory by TMA (every scene size, and the
- * accelerated mode), or read from the launch's constant bank (<= RT_CONST_MAX_SPHERES records). */
-template <int MIN_BLOCKS, int NSLOTS, bool ACCEL>
+/* The entry points: records staged in shared memory by TMA (every scene size, and the accelerated
+ * mode), or read from the launch's constant bank (<= RT_CONST_MAX_SPHERES records); slot records in
+ * shared memory (SMEM_SLOTS) or in local memory. */
+template <int MIN_BLOCKS, int NSLOTS, bool ACCEL, bool SMEM_SLOTS>
 __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel(const __grid_constant__ TraceParams p) {
-  trace_body<false, NSLOTS, ACCEL>(p, *reinterpret_cast<const ConstRecords*>(0));   /* never read without USE_CONST */
+  trace_body<false, NSLOTS, ACCEL, SMEM_SLOTS>(p, *reinterpret_cast<const ConstRecords*>(&p));   /* never read without USE_CONST */
 }
-template <int MIN_BLOCKS, int NSLOTS>
+template <int MIN_BLOCKS, int NSLOTS, bool SMEM_SLOTS>
 __global__ void __launch_bounds__(RT_BLOCK, MIN_BLOCKS) trace_kernel_const(const __grid_constant__ TraceParams p,
                                                                           const __grid_constant__ ConstRecords c) {
-  trace_body<true, NSLOTS, false>(p, c);
+  trace_body<true, NSLOTS, false, SMEM_SLOTS>(p, c);
 }
 
 /* Sum each pixel's samples in the reference's order (main.cpp:430-447) and take the frame's
@@ -1137,7 +1332,7 @@ __global__ void combine_kernel(const float4* __restrict__ samples, float4* __res
   for (uint32_t px = blockIdx.x * blockDim.x + threadIdx.x; px < npix; px += stride) {
     V3 acc = mk(0.f, 0.f, 0.f);
     for (uint32_t k = 0; k < spp; ++k) {
-      const float4 v = samples[(size_t)px * spp + k];
+      const float4 v = __ldcs(&samples[(size_t)px * spp + k]);
       acc = vadd(acc, mk(v.x, v.y, v.z));
     }
     fb[px] = make_float4(acc.x, acc.y, acc.z, 1.f);

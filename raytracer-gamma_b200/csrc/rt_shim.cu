@@ -26,6 +26,7 @@ struct rt_cuda_ctx {
   int device = 0;
   int smCount = 0;
   int smemOptin = 0;               /* largest dynamic shared memory one CTA may ask for */
+  int smemPerSM = 0;
   cudaStream_t stream = nullptr;
   bool ownStream = false;
   cudaEvent_t ev0 = nullptr, ev1 = nullptr;
@@ -70,7 +71,10 @@ struct rt_cuda_ctx {
   unsigned nextTicket = 0;
 
   /* options */
-  int staging = 0, noFilter = 0, blocksPerSM = 0, minBlocks = 0, slots = 0, prefetch = 0;
+  int staging = 0, noFilter = 0, blocksPerSM = 0, slots = 0;
+  int rebalance = 1;               /* drain balancing (rt_kernels.cuh rebalance) */
+  int sparseBelow = 12;            /* sparse rounds for the last queries of a warp (rt_kernels.cuh sparse_query) */
+  int slotMode = 0;                /* 0 auto | 1 slot records in shared memory | 2 in local memory */
   int accel = 0;                   /* 1: two-level cluster filter (optional accelerated mode) */
   uint32_t nc = 0, ncPad = 0;
 
@@ -146,6 +150,7 @@ extern "C" int rt_cuda_init(int device, rt_cuda_ctx** out) {
   }
   ctx->smCount = pr.multiProcessorCount;
   ctx->smemOptin = (int)pr.sharedMemPerBlockOptin;
+  ctx->smemPerSM = (int)pr.sharedMemPerMultiprocessor;
   if (cudaStreamCreateWithFlags(&ctx->stream, cudaStreamNonBlocking) != cudaSuccess) return fail(RT_CUDA_ERR_CUDA);
   ctx->ownStream = true;
   if (cudaStreamCreateWithFlags(&ctx->copyStream, cudaStreamNonBlocking) != cudaSuccess) return fail(RT_CUDA_ERR_CUDA);
@@ -214,10 +219,11 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
   if (!strcmp(key, "accel")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->accel = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
-#ifdef RT_DEV_VARIANTS   /* development builds only: register-budget / slot-count variants of the trace kernel */
-  if (!strcmp(key, "prefetch")) { ctx->prefetch = value ? 1 : 0; return RT_CUDA_OK; }
-  if (!strcmp(key, "slots")) { if (value != 0 && (value < 2 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->slots = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "min_blocks")) { if (value != 0 && (value < 2 || value > 3)) return RT_CUDA_ERR_INVALID_ARG; ctx->minBlocks = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "rebalance")) { ctx->rebalance = value ? 1 : 0; return RT_CUDA_OK; }
+  if (!strcmp(key, "sparse_below")) { if (value < 0 || value > 64) return RT_CUDA_ERR_INVALID_ARG; ctx->sparseBelow = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "slot_mode")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->slotMode = (int)value; return RT_CUDA_OK; }
+#ifdef RT_DEV_VARIANTS   /* development builds only: slot-count variants of the local-memory kernel */
+  if (!strcmp(key, "slots")) { if (value != 0 && (value < 3 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->slots = (int)value; return RT_CUDA_OK; }
 #endif
   return RT_CUDA_ERR_INVALID_ARG;
 }
@@ -253,7 +259,7 @@ extern "C" int rt_cuda_upload_scene(rt_cuda_ctx* ctx, const rt_sphere* spheres, 
                                     const rt_light* lights, unsigned lgtNum) {
   if (!ctx) return RT_CUDA_ERR_INVALID_ARG;
   if ((sphNum && !spheres) || (lgtNum && !lights)) return RT_CUDA_ERR_INVALID_ARG;
-  if (sphNum > RT_CUDA_MAX_SPHERES) return RT_CUDA_ERR_TOO_LARGE;
+  if (sphNum > RT_CUDA_MAX_SPHERES || lgtNum > RT_CUDA_MAX_LIGHTS) return RT_CUDA_ERR_TOO_LARGE;
   CU(cudaSetDevice(ctx->device));
   ctx->haveScene = false;
   ctx->hSpheres.assign(spheres, spheres + sphNum);
@@ -309,7 +315,7 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   const uint32_t spp = (uint32_t)spp64;
 
   /* the accelerated mode needs something to cull, its records in shared memory, and the cluster form */
-  const size_t perCta = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short) + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float) + 16;
+  const size_t listBytes = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short);
   const uint32_t list1Max = (ctx->n >= 2048u) ? RT_LIST1_LARGE : RT_LIST1_SMALL;
   const bool wantAccel = ctx->accel && !ctx->noFilter && ctx->n >= (ctx->accel == 2 ? 4u * RT_CLUSTER : RT_ACCEL_MIN_SPHERES);
   if (wantAccel && !ctx->haveClusters) {       /* option set after the upload: add the cluster form now */
@@ -318,7 +324,7 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   }
   const size_t accelBytes = (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) + (size_t)list1Max * RT_BLOCK * sizeof(unsigned short);
   /* ... and falls back to the plain mode when they do not fit one CTA (> ~8 000 spheres) */
-  const bool accel = wantAccel && ctx->haveClusters && perCta + accelBytes <= (size_t)ctx->smemOptin;
+  const bool accel = wantAccel && ctx->haveClusters && 16 + listBytes + accelBytes <= (size_t)ctx->smemOptin;
 
   /* staging: shared memory filled by TMA bulk copies is the default at every size (it is equal or faster
    * than the constant bank from 16 spheres up, profiles/r1/sweep_config5.jsonl); option staging=1 selects
@@ -329,26 +335,31 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if (accel) staging = 2;
   const bool useConst = (staging == 1);
   const size_t sceneBytes = useConst ? 0 : accel ? (size_t)ctx->ncPad * (16 + RT_CLUSTER * 18) : (size_t)ctx->nPad * 16;
-  const size_t smem = 16 + sceneBytes + (accel ? (size_t)list1Max * RT_BLOCK * sizeof(unsigned short) : 0)
-                      + (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)
-                      + (size_t)4 * RT_SHADOW_BATCH * RT_BLOCK * sizeof(float);
+  const size_t smemBase = 16 + sceneBytes + (accel ? (size_t)list1Max * RT_BLOCK * sizeof(unsigned short) : 0) + listBytes;
+  /* slot records on chip whenever two CTAs per SM still fit: four slots per lane, else three; else local memory */
+  const size_t slotBytes1 = (size_t)RT_SLOT_WORDS * RT_BLOCK * sizeof(uint32_t);
+  const size_t perCtaMax = (size_t)ctx->smemPerSM / RT_DEFAULT_MIN_BLOCKS - 1024;      /* 1 KB per CTA is reserved by the system */
+  int smemSlots = 0;                 /* 0 = local memory, else the slot count */
+  if (!accel && ctx->slotMode != 2) {
+    for (int ns = RT_SLOTS; ns >= 3 && !smemSlots; --ns) {
+      const size_t need = smemBase + slotBytes1 * ns;
+      if (need <= (size_t)ctx->smemOptin && (need <= perCtaMax || (ctx->slotMode == 1 && ns == 3))) smemSlots = ns;
+    }
+#ifdef RT_DEV_VARIANTS
+    if (ctx->slots == 3 && smemSlots == 4) smemSlots = 3;
+#endif
+  }
+  const size_t smem = smemBase + slotBytes1 * smemSlots;
 
   void (*kern)(const TraceParams) = nullptr;
   void (*kernC)(const TraceParams, const ConstRecords) = nullptr;
-#ifdef RT_DEV_VARIANTS
-  const int minBlocks = ctx->minBlocks ? ctx->minBlocks : RT_DEFAULT_MIN_BLOCKS;
-  const int nslots = ctx->slots ? ctx->slots : RT_DEFAULT_SLOTS;
-#define RT_PICK(M) ((nslots == 2) ? trace_kernel<M, 2, false> : (nslots == 3) ? trace_kernel<M, 3, false> : trace_kernel<M, 4, false>)
-#define RT_PICKC(M) ((nslots == 2) ? trace_kernel_const<M, 2> : (nslots == 3) ? trace_kernel_const<M, 3> : trace_kernel_const<M, 4>)
-  if (useConst) kernC = (minBlocks == 2) ? RT_PICKC(2) : RT_PICKC(3);
-  else          kern = (minBlocks == 2) ? RT_PICK(2) : RT_PICK(3);
-#undef RT_PICK
-#undef RT_PICKC
-#else
-  if (useConst) kernC = trace_kernel_const<RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS>;
-  else          kern = trace_kernel<RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS, false>;
-#endif
-  if (accel) { kern = trace_kernel<RT_DEFAULT_MIN_BLOCKS, RT_DEFAULT_SLOTS, true>; kernC = nullptr; }
+  if (accel) kern = trace_kernel<RT_DEFAULT_MIN_BLOCKS, RT_SLOTS, true, false>;
+  else if (useConst) kernC = smemSlots == 4 ? trace_kernel_const<RT_DEFAULT_MIN_BLOCKS, 4, true>
+                           : smemSlots == 3 ? trace_kernel_const<RT_DEFAULT_MIN_BLOCKS, 3, true>
+                                            : trace_kernel_const<RT_DEFAULT_MIN_BLOCKS, RT_SLOTS, false>;
+  else kern = smemSlots == 4 ? trace_kernel<RT_DEFAULT_MIN_BLOCKS, 4, false, true>
+            : smemSlots == 3 ? trace_kernel<RT_DEFAULT_MIN_BLOCKS, 3, false, true>
+                             : trace_kernel<RT_DEFAULT_MIN_BLOCKS, RT_SLOTS, false, false>;
   const void* kfn = kernC ? (const void*)kernC : (const void*)kern;
   int perSM = 0;
   uint32_t grid = 0, totalWork = 0;
@@ -397,7 +408,8 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   p.spp = spp;
   p.samples = (spp > 1) ? ctx->dSamples : nullptr;
   p.noFilter = ctx->noFilter;
-  p.prefetch = ctx->prefetch;
+  p.rebalance = ctx->rebalance;
+  p.sparseBelow = (uint32_t)ctx->sparseBelow;
   p.list1Max = list1Max;
   /* queue granule: small enough to balance the tail, large enough to amortise the atomic */
   const uint32_t warps = grid * (RT_BLOCK / 32);
@@ -422,6 +434,7 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   ctx->stats.clusters = accel ? ctx->nc : 0u;
   ctx->stats.grid = grid; ctx->stats.block = RT_BLOCK; ctx->stats.smem_bytes = (uint32_t)smem;
   ctx->stats.staging = (uint32_t)staging;
+  ctx->stats.slots_on_chip = (uint32_t)smemSlots;
   ctx->haveFrame = true;
   return RT_CUDA_OK;
 }
@@ -630,6 +643,7 @@ extern "C" int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out) {
   s.served_trace = c[7]; s.served_shadow = c[8]; s.served_contain = c[9]; s.passes = c[11];
   s.passes_trace = c[12]; s.passes_shadow2 = c[13]; s.passes_shadow4 = c[14]; s.passes_contain = c[15];
   for (int i = 0; i < 6; ++i) s.phase_cycles[i] = c[16 + i];
+  s.sparse_queries = c[22]; s.migrated_slots = (uint32_t)c[23];
   s.filter_tests = ctx->noFilter ? 0 : c[10] * (unsigned long long)(s.accel ? ctx->ncPad : ctx->nPad);   /* accelerated mode: cluster tests only */
   s.sph_num = ctx->n; s.sph_padded = ctx->nPad; s.lgt_num = ctx->nl;
   s.width = ctx->W; s.height = ctx->H; s.local_rows = ctx->localRows;

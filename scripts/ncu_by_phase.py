@@ -26,10 +26,14 @@ if args.root:
     ROOT = Path(args.root).resolve()
     CSRC = ROOT / "raytracer-gamma_b200" / "csrc"
 
-rows = list(csv.reader(open(args.sass_csv)))
-kname = rows[0][1]
-hdr, data = rows[1], rows[2:]
-ix = {n: i for i, n in enumerate(hdr)}
+STATIC = args.sass_csv == "-"        # no capture: static instruction counts per phase only (needs --kernel)
+if STATIC:
+    kname, hdr, data, ix = args.kernel, [], None, {}
+else:
+    rows = list(csv.reader(open(args.sass_csv)))
+    kname = rows[0][1]
+    hdr, data = rows[1], rows[2:]
+    ix = {n: i for i, n in enumerate(hdr)}
 
 cubin = args.cubin
 if not cubin:
@@ -76,6 +80,8 @@ for line in dis.split("\n"):
         continue
     if re.match(r"\s+/\*[0-9a-f]{4,6}\*/", line):
         insts.append((frames, sub))
+if STATIC:
+    data = [None] * len(insts)
 assert len(insts) == len(data), (len(insts), len(data), "the cubin is not the captured build")
 
 def funcs_of(path):
@@ -95,17 +101,28 @@ def fn_at(f, l):
     return FN[f][j][1] if j >= 0 else None
 KERNEL_FUNCS = {"trace_body", "trace_kernel", "trace_kernel_const", "__launch_bounds__"}
 
-def sub_phase(f, l, fn):
-    """inside pass_*: set-up / loop / gather-call / resolve by looking backwards for the enclosing marker"""
+def lambda_kind(f, l):
+    """a line inside one of the pass lambdas: which one?  (looks backwards for the lambda header)"""
     src = SRC[f]
-    for k in range(l - 1, max(0, l - 200), -1):
+    for k in range(l - 1, max(0, l - 120), -1):
         t = src[k]
-        if re.search(r"for \(uint32_t base|for \(; base < nPad", t): return "filter loop"
-        if re.search(r"for \(int k = 0; k < maxc", t): return "resolve" if "maxc2" in t or "accel" not in fn else "members"
-        if re.search(r"const unsigned comb", t) and k < l - 1: return "loop exit / gather call"
-        if re.search(r"if \(overflow\)", t): return "epilogue"
-        if re.search(r"__device__ __forceinline__ void pass_", t): return "set-up"
-    return "set-up"
+        if "[&](uint32_t base)" in t: return "filter loop"
+        if "[&](uint32_t e)" in t: return "resolve"
+        if "[&](uint32_t cl" in t: return "members"
+        if re.search(r"filter_rounds<|accel_rounds<", t): return None
+        if re.search(r"__device__ __forceinline__ void pass_", t): return None
+    return None
+
+def rounds_phase(f, l):
+    """a line of filter_rounds / accel_rounds itself"""
+    src = SRC[f]
+    for k in range(l - 1, max(0, l - 80), -1):
+        t = src[k]
+        if re.search(r"for \(int (k|j) = 0", t) or "resolve(" in t: return "resolve"
+        if "members(" in t: return "members"
+        if re.search(r"for \((uint32_t base|; base < nPad)", t): return "filter loop"
+        if "__device__ __forceinline__ void" in t: return "filter loop"
+    return "filter loop"
 
 def kernel_phase(l):
     src = SRC["rt_kernels.cuh"]
@@ -115,34 +132,46 @@ def kernel_phase(l):
         if "---- advance the served slots" in t: return "kernel: advance glue"
         if "---- vote ----" in t: return "kernel: vote + dispatch"
         if "---- refill ----" in t: return "kernel: refill"
-        if "trace_body(" in t or "trace_kernel(" in t: return "kernel: prologue"
+        if "void trace_body(" in t: return "kernel: prologue"
     return "kernel: other"
+
+ADVANCE = ("advance_slot", "advance", "after_matte", "after_contain", "unwind", "fresnel_term", "setup_shadow_batch",
+           "load_slot", "store_slot", "sample_value")
 
 def classify(frames, sub):
     if sub:
         d = demangle(sub)
         return "out-of-line: " + re.sub(r"\(.*", "", d).replace("rtg::", "")
     chain = list(reversed(frames))          # outermost first
-    for f, l in chain:
-        fn = fn_at(f, l)
+    fns = [(f, l, fn_at(f, l)) for f, l in chain]
+    names = [fn for _, _, fn in fns]
+    if any(fn in ("gather", "gather1", "gather2") for fn in names):
+        return "gather"
+    for f, l, fn in fns:
         if fn is None or fn in KERNEL_FUNCS:
             continue
         if fn.startswith("pass_"):
-            return f"{fn}: {sub_phase(f, l, fn)}"
-        if fn in ("gather", "gather1", "gather2", "member_bits"):
-            return "gather"
-        if fn in ("advance_slot", "advance", "after_matte", "after_contain", "unwind", "fresnel_term", "setup_shadow_batch"):
+            # the deepest frame that still lies in this pass function decides (lambda bodies are lines of pass_*)
+            deep = [(ff, ll) for ff, ll, nn in fns if nn == fn]
+            kind = lambda_kind(*deep[-1])
+            if kind is None and any(nn in ("filter_rounds", "accel_rounds") for nn in names):
+                fr = [(ff, ll) for ff, ll, nn in fns if nn in ("filter_rounds", "accel_rounds")][-1]
+                kind = rounds_phase(*fr)
+            if kind is None:
+                kind = "set-up / epilogue"
+            return f"{fn}: {kind}"
+        if fn in ADVANCE:
             return "advance (state machine)"
         if fn in ("start_task", "work_to_task", "set_trace_query"):
             return "kernel: refill"
         return "other: " + fn
-    f, l = chain[0] if chain else ("?", 0)
-    return kernel_phase(l) if f == "rt_kernels.cuh" else "kernel: other"
+    inner = [(f, l) for f, l, fn in fns if fn == "trace_body"]
+    return kernel_phase(inner[-1][1]) if inner else "kernel: other"
 
 inst = collections.Counter(); samp = collections.Counter(); thr = collections.Counter(); byline = collections.Counter(); static = collections.Counter()
 ti = ts = 0
 for r, (frames, sub) in zip(data, insts):
-    a = int(r[ix["Instructions Executed"]]); b = int(r[ix["# Samples"]]); t = int(r[ix["Thread Instructions Executed"]])
+    a, b, t = (1, 1, 32) if STATIC else (int(r[ix["Instructions Executed"]]), int(r[ix["# Samples"]]), int(r[ix["Thread Instructions Executed"]]))
     key = classify(frames, sub)
     inst[key] += a; samp[key] += b; thr[key] += t; ti += a; ts += b; static[key] += 1
     if frames:

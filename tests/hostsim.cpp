@@ -165,6 +165,12 @@ extern "C" int hostsim_render(const rt_sphere* spheres, unsigned n, const rt_lig
             if (mode >= 2) answer_accel(s, sc, ctr, sg, mode == 3, clusterOf, c[8], c[9]);
             else answer(s, sc, ctr, mode == 1, sg);
             if (advance(s, stack, ctr, sc, cam, &sg)) break;
+            /* between two passes the kernel keeps only the 21-word record (slot_pack / slot_unpack):
+             * everything the record drops must really be dead */
+            uint32_t rec[RT_SLOT_WORDS];
+            slot_pack<1>(rec, s);
+            memset(&s, 0xA5, sizeof s);
+            slot_unpack<1>(rec, s);
           }
           samples[count++] = sample_value(s, cam);
         }

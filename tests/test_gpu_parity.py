@@ -284,6 +284,30 @@ def test_async_readback_overlaps_and_matches(pkg, orc_mod, oracle, gpu):
     hb.free()
 
 
+def test_filter_bound_fuzz(pkg):
+    """The FMA filter of rt_core.cuh may only rule out (query, sphere) pairs the reference's exact expressions
+    reject too.  > 10^9 adversarial pairs on the GPU (tests/fuzz_filter.cu: coordinates to 10^4, radii over six
+    decades, rays grazing the silhouette within a relative 10^-8 .. 10^-1, unit and unnormalised directions,
+    containment probes on the surface): zero violations, and the filter still rejects most pairs."""
+    import ctypes
+    import sys
+    graft = sys.modules["__graft_entry__"]
+    lib = ctypes.CDLL(str(graft.build_fuzz()))
+    lib.fuzz_filter.argtypes = [ctypes.c_uint64, ctypes.c_uint32, ctypes.c_uint32, ctypes.c_float, ctypes.c_float,
+                                ctypes.c_float, ctypes.POINTER(ctypes.c_uint64)]
+    total = 0
+    for seed, max_log, r_lo, r_hi in [(1, 4.0, -3.0, 3.0), (2, 1.5, -1.0, 1.0), (3, 4.0, -3.0, 0.0), (4, 3.0, 0.0, 3.0)]:
+        out = (ctypes.c_uint64 * 9)()
+        assert lib.fuzz_filter(seed, 1 << 18, 600, max_log, r_lo, r_hi, out) == 0
+        rays, cand, hits, viol, refused, probes, pcand, inside, pviol = [int(v) for v in out]
+        assert viol == 0 and pviol == 0, (seed, list(out))
+        assert rays == probes == (1 << 18) * 600
+        assert hits > 0.2 * rays and inside > 0.3 * probes          # the generator really aims at the surface
+        assert refused < 0.01 * rays
+        total += rays + probes
+    assert total >= 1_000_000_000
+
+
 def _needs_gpus(pkg, n):
     if pkg.device_count() < n:
         pytest.skip(f"needs {n} GPUs on this box")
