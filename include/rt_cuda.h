@@ -59,7 +59,7 @@ typedef enum rt_cuda_status {
 /* Limits of this implementation */
 #define RT_CUDA_MAX_SPHERES 12288u   /* filter records must fit one SM's shared memory */
 #define RT_CUDA_MAX_STACK   16       /* RTSTACK_MAXSIZE values accepted by rt_cuda_render */
-#define RT_CUDA_MAX_LIGHTS  1048576u /* the slot record keeps the light index in 22 bits */
+#define RT_CUDA_MAX_LIGHTS  32767u   /* the slot record keeps the light index in 15 bits */
 
 /* Counters and timings of the last render (device-side tallies). */
 typedef struct rt_cuda_stats {
@@ -87,8 +87,6 @@ typedef struct rt_cuda_stats {
   uint32_t accel;           /* 1 = this frame used the two-level cluster filter (option "accel")    */
   uint32_t clusters;        /* ... over this many sphere clusters                                   */
   uint32_t slots_on_chip;   /* slot records per lane held in shared memory (4 or 3), 0 = they lived in local memory */
-  uint32_t migrated_slots;  /* drain balancing: slots handed from a busy lane to an idle one                     */
-  uint64_t sparse_queries;  /* sub-queries served in sparse rounds (one query, spheres spread over the lanes)    */
 } rt_cuda_stats;
 
 /* Open device `device` (cudaSetDevice ordinal).  *out receives the context. */
@@ -156,9 +154,6 @@ int rt_cuda_flush_l2(rt_cuda_ctx* ctx);
 /* Tuning / debug switches: "staging" 0 auto (= 2) | 1 constant bank: the filter records travel as a
  *   __grid_constant__ launch parameter, <= 1024 spheres | 2 shared memory filled by TMA bulk copies;
  * "no_filter" 1 = exact test against every sphere; "blocks_per_sm" 0 auto;
- * "rebalance" 1 (default) | 0: lanes of a warp hand slots to each other once the tile queue is dry;
- * "sparse_below" (default 12, 0 = off): a drained warp with at most this many queries left serves them one at
- *   a time with the spheres spread over its lanes;
  * "slot_mode" 0 auto (slot records in shared memory whenever two CTAs per SM still fit) | 1 shared | 2 local;
  * (development builds, -DRT_DEV_VARIANTS: "slots" 3 | 4 for the local-memory kernel);
  * "accel" 0 off | 1 = two-level cluster filter where it pays (>= 768 spheres) | 2 = from 32 spheres.

@@ -108,7 +108,6 @@ class Stats(ctypes.Structure):
         ("grid", ctypes.c_uint32), ("block", ctypes.c_uint32), ("smem_bytes", ctypes.c_uint32),
         ("staging", ctypes.c_uint32), ("engine", ctypes.c_uint32),
         ("accel", ctypes.c_uint32), ("clusters", ctypes.c_uint32), ("slots_on_chip", ctypes.c_uint32),
-        ("migrated_slots", ctypes.c_uint32), ("sparse_queries", ctypes.c_uint64),
     ]
 
     def as_dict(self) -> dict:

@@ -319,6 +319,8 @@ struct Slot {
   int obj;                /* struck sphere */
   int light;              /* first light of the current shadow batch */
   int ndirs;              /* directions in the pending query (1 for a trace ray) */
+  int count;              /* queries of this sample answered so far, saturating at RT_COUNT_MAX (work order, see WorkMap) */
+  int first;              /* 1: the sample belongs to its tile's FIRST group, whose chain lengths order the tile's other groups */
   V3 result;              /* "colourSum" of raytracer.h:425 */
   V3 colour, rayD, rayI;  /* the call being evaluated ("currSnapshot") */
   V3 P, Nrm;              /* its hit */
@@ -336,7 +338,7 @@ struct Slot {
 
 /* ---- slot records: how a slot is kept between two passes (21 words) ------------------------
  * word 0      pixel (index of the sample's result record, 0xFFFFFFFF = free slot)
- * word 1      kind | ndirs << 2 | (top + 1) << 5 | light << 10
+ * word 1      kind | ndirs << 2 | (top + 1) << 5 | light << 10 (15 bits) | count << 25 (6 bits) | first << 31
  * word 2      medium | obj << 16
  * words 3..   result, rayD, rayI, P, Nrm, lit|colour (3 words each).  While a TRACE query is pending the
  *             hit fields are dead and the P words hold the ray's origin; the probe point of a CONTAIN
@@ -348,6 +350,7 @@ struct Slot {
  * registers.  STRIDE = distance in words between consecutive record words (1, or the CTA size when the
  * records of a CTA are interleaved in shared memory). */
 #define RT_SLOT_WORDS 21
+#define RT_COUNT_MAX 63
 enum { W_PIXEL = 0, W_HDR = 1, W_MEDOBJ = 2, W_RESULT = 3, W_RAYD = 6, W_RAYI = 9, W_P = 12, W_NRM = 15, W_LITCOL = 18 };
 #if defined(__CUDA_ARCH__)
 RT_HD uint32_t f2u(float f) { return __float_as_uint(f); }
@@ -364,7 +367,8 @@ template <int STRIDE> RT_HD void rec_stv(uint32_t* r, int wd, V3 v) {
 }
 template <int STRIDE> RT_HD void slot_pack(uint32_t* r, const Slot& s) {
   r[W_PIXEL * STRIDE] = s.pixel;
-  r[W_HDR * STRIDE] = (uint32_t)s.kind | ((uint32_t)s.ndirs << 2) | ((uint32_t)(s.top + 1) << 5) | ((uint32_t)s.light << 10);
+  r[W_HDR * STRIDE] = (uint32_t)s.kind | ((uint32_t)s.ndirs << 2) | ((uint32_t)(s.top + 1) << 5) | ((uint32_t)s.light << 10) |
+                      ((uint32_t)s.count << 25) | ((uint32_t)s.first << 31);
   r[W_MEDOBJ * STRIDE] = ((uint32_t)s.medium & 0xFFFFu) | ((uint32_t)s.obj << 16);
   rec_stv<STRIDE>(r, W_RESULT, s.result);
   rec_stv<STRIDE>(r, W_RAYD, s.rayD); rec_stv<STRIDE>(r, W_RAYI, s.rayI);
@@ -375,7 +379,8 @@ template <int STRIDE> RT_HD void slot_pack(uint32_t* r, const Slot& s) {
 template <int STRIDE> RT_HD void slot_unpack(const uint32_t* r, Slot& s) {
   s.pixel = r[W_PIXEL * STRIDE];
   const uint32_t h = r[W_HDR * STRIDE], mo = r[W_MEDOBJ * STRIDE];
-  s.kind = (int)(h & 3u); s.ndirs = (int)((h >> 2) & 7u); s.top = (int)((h >> 5) & 31u) - 1; s.light = (int)(h >> 10);
+  s.kind = (int)(h & 3u); s.ndirs = (int)((h >> 2) & 7u); s.top = (int)((h >> 5) & 31u) - 1; s.light = (int)((h >> 10) & 0x7FFFu);
+  s.count = (int)((h >> 25) & 63u); s.first = (int)(h >> 31);
   s.medium = (int)(mo & 0xFFFFu); s.obj = (int)(mo >> 16);
   s.result = rec_ldv<STRIDE>(r, W_RESULT);
   s.rayD = rec_ldv<STRIDE>(r, W_RAYD); s.rayI = rec_ldv<STRIDE>(r, W_RAYI);
@@ -409,6 +414,65 @@ RT_HD Camera make_camera(uint32_t W, uint32_t H, float zoom, float alias, int S,
   return c;
 }
 
+
+/* ---- work items -----------------------------------------------------------------
+ * A work item is one sample of one pixel; 32 consecutive items form a GROUP (tile, k):
+ *   spp > 1:  tile = 8x4 pixels, k = sample index (K = spp groups per tile);
+ *   spp == 1: tile = 16x8 pixels, k = one of its four stride-2 sub-lattices (K = 4) —
+ * either way the groups of a tile see almost the same geometry, so the chain lengths measured on group 0
+ * predict the others: the kernel hands out every tile's group 0 first and then the remaining groups
+ * deepest tiles first (longest-processing-time order; the last samples of a launch are then short ones
+ * and the launch does not end on a few warps working off 100-query chains).  Rows are the context's LOCAL
+ * rows (strip r of the frame is ours iff r % stripStride == stripFirst). */
+struct WorkMap {
+  uint32_t W, localRows, stripRows, stripFirst, stripStride;
+  uint32_t spp, nIter, K, lattice, tilesX, tilesY, nTiles;
+};
+RT_HD WorkMap make_workmap(uint32_t W, uint32_t localRows, uint32_t stripRows, uint32_t stripFirst, uint32_t stripStride,
+                           uint32_t spp, uint32_t nIter) {
+  WorkMap m;
+  m.W = W; m.localRows = localRows; m.stripRows = stripRows; m.stripFirst = stripFirst; m.stripStride = stripStride;
+  m.spp = spp; m.nIter = nIter;
+  m.lattice = (spp == 1u) ? 1u : 0u;
+  m.K = m.lattice ? 4u : spp;
+  m.tilesX = m.lattice ? (W + 15u) / 16u : (W + 7u) / 8u;
+  m.tilesY = m.lattice ? (localRows + 7u) / 8u : (localRows + 3u) / 4u;
+  m.nTiles = m.tilesX * m.tilesY;
+  return m;
+}
+/* item `within` (0..31) of group (tile, k): frame pixel (gx, gy), index of the result record, sample (si, sj).
+ * false = the item lies outside the frame. */
+RT_HD bool work_item(const WorkMap& m, uint32_t tile, uint32_t k, uint32_t within, uint32_t& gx, uint32_t& gy,
+                     uint32_t& dst, int& si, int& sj) {
+  const uint32_t ty = tile / m.tilesX, tx = tile - ty * m.tilesX;
+  uint32_t x, y;
+  if (m.lattice) { x = tx * 16u + 2u * (within & 7u) + (k & 1u); y = ty * 8u + 2u * (within >> 3) + (k >> 1); }
+  else           { x = tx * 8u + (within & 7u);                 y = ty * 4u + (within >> 3); }
+  if (x >= m.W || y >= m.localRows) return false;
+  const uint32_t strip = y / m.stripRows;
+  gx = x;
+  gy = (strip * m.stripStride + m.stripFirst) * m.stripRows + (y - strip * m.stripRows);
+  if (m.lattice) { dst = y * m.W + x; si = 0; sj = 0; }
+  else {
+    dst = (y * m.W + x) * m.spp + k;
+    si = (int)(k / m.nIter);
+    sj = (int)(k - (uint32_t)si * m.nIter);
+  }
+  return true;
+}
+/* the tile a result record belongs to */
+RT_HD uint32_t tile_of_dst(const WorkMap& m, uint32_t dst) {
+  const uint32_t pix = m.lattice ? dst : dst / m.spp;
+  const uint32_t y = pix / m.W, x = pix - y * m.W;
+  return m.lattice ? (y >> 3) * m.tilesX + (x >> 4) : (y >> 2) * m.tilesX + (x >> 3);
+}
+/* work order classes: a tile whose first group showed chains of >= RT_DEEP_AT queries goes out first */
+#define RT_ORDER_CLASSES 5
+#define RT_DEEP_AT 32
+RT_HD uint32_t order_class(uint32_t maxCount) {
+  return maxCount >= RT_DEEP_AT ? 0u : maxCount >= 16u ? 1u : maxCount >= 8u ? 2u : maxCount >= 2u ? 3u : 4u;
+}
+
 /* The caller has already made `d` the current call's direction (s.rayD). */
 RT_HD void set_trace_query(Slot& s, Counters& ctr, V3 o, V3 d) {
   s.kind = K_TRACE;
@@ -435,6 +499,7 @@ RT_HD void start_task(Slot& s, Counters& ctr, const Camera& cam, uint32_t gx, ui
   s.result = mk(0.f, 0.f, 0.f);
   s.medium = cam.ambient;                  /* every sample starts in the ambient medium, main.cpp:439 */
   s.top = -1;
+  s.count = 0; s.first = 0;
   ctr.samples++;
   set_trace_query(s, ctr, mk(0.f, 0.f, 0.f), d);
 }
@@ -639,6 +704,7 @@ RT_HD int after_matte(Slot& s, Counters& ctr, const SceneView& sc, bool haveMatt
 RT_HD bool advance(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, const Camera& cam,
                    const ShadowGeo* sg) {
   int act;
+  if (s.count < RT_COUNT_MAX) ++s.count;
   if (s.kind == K_TRACE) {
     ctr.rays++;
     if (s.hitIdx < 0) {

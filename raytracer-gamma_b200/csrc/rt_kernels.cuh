@@ -67,11 +67,19 @@ namespace rtg {
 #define RT_CONST_MAX_SPHERES 1024
 #define RT_NUM_COUNTERS 24
 #define RT_NO_PIXEL 0xFFFFFFFFu
+#define RT_FULL 0xFFFFFFFFu
+#define RT_NONE 0xFFFFFFFFu
 #ifndef RT_ADV_CONVERGENT
-#define RT_ADV_CONVERGENT 1      /* write the slot record back after the warp has reconverged (see advance_slot) */
+#define RT_ADV_CONVERGENT 0      /* write the slot record back after the warp has reconverged (see advance_slot) */
 #endif
 #ifndef RT_SHADOW_INLINE_NORM
-#define RT_SHADOW_INLINE_NORM 1  /* the four normalisations of a shadow batch inline (they overlap) rather than out of line */
+#define RT_SHADOW_INLINE_NORM 0  /* the four normalisations of a shadow batch inline (they overlap) rather than out of line */
+#endif
+#ifndef RT_LOCKSTEP
+#define RT_LOCKSTEP 0            /* 1 | 2: groups of warps start every pass together (see trace_body) */
+#endif
+#ifndef RT_LOCK_WARPS
+#define RT_LOCK_WARPS 8          /* warps per lockstep group (8 = the CTA) */
 #endif
 #define RT_SLOTS 4               /* slots per lane (3 in shared memory when 4 do not fit beside the filter records) */
 
@@ -84,12 +92,16 @@ struct TraceParams {
   unsigned int* workCounter;/* tile queue head                                      */
   unsigned int* maxBits;    /* running max of positive channel values (float bits)  */
   unsigned long long* counters;  /* [RT_NUM_COUNTERS], see rt_shim.cu                */
-  uint32_t localRows;       /* rows rendered by this context                        */
-  uint32_t stripRows, stripFirst, stripStride;   /* row r is ours iff (r/stripRows)%stripStride==stripFirst */
-  uint32_t tilesX, totalWork, chunk;
+  WorkMap wm;               /* work items -> pixels and samples (rt_core.cuh)        */
+  uint32_t total1, chunk;   /* items the queue head hands out (all of them, or the tiles' first groups), queue granule */
+  /* longest-chains-first work order (lpt = 1): see "Work order" below */
+  uint32_t lpt, kPerBlock, nBlocks, nEntries;
+  unsigned int* tileMax;    /* [nTiles] longest chain (queries) seen in the tile's first group      */
+  unsigned int* tileDone;   /* [nTiles] items of the first group that are finished (32 = all)        */
+  unsigned int* tilePushed; /* [nTiles] 1 once the tile's other groups are in a bucket               */
+  unsigned int* bucketEntries;   /* [RT_ORDER_CLASSES][nEntries] entry + 1 (0 = not written yet)     */
+  unsigned int* bucketCtl;  /* [0..4] tails, [8..12] heads, [16] entries handed out                  */
   int noFilter;             /* debug: exact test for every sphere                   */
-  int rebalance;            /* drain balancing on (default) / off (option "rebalance")   */
-  uint32_t sparseBelow;     /* a drained warp with at most this many queries left serves them in sparse rounds (0 = never) */
   uint32_t list1Max;        /* accelerated mode: capacity of the per-lane (sub, cluster) lists */
 };
 
@@ -133,24 +145,57 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
       : "memory");
 }
 
-/* Map a queue index to a work item = one sample of one pixel.  Pixels are walked in 8x4
- * tiles (row-major inside, tiles row-major); 32 consecutive indices are the 32 pixels of a
- * tile for one sample, the next 32 the same tile's next sample. */
-__device__ __forceinline__ bool work_to_task(const TraceParams& p, uint32_t idx, uint32_t& gx,
-                                             uint32_t& gy, uint32_t& dst, int& si, int& sj) {
-  const uint32_t grp = idx >> 5, within = idx & 31u;
-  const uint32_t tile = grp / p.spp, k = grp - tile * p.spp;
-  const uint32_t ty = tile / p.tilesX, tx = tile - ty * p.tilesX;
-  const uint32_t x = tx * 8u + (within & 7u);
-  const uint32_t y = ty * 4u + (within >> 3);
-  if (x >= p.cam.W || y >= p.localRows) return false;
-  const uint32_t strip = y / p.stripRows;
-  gx = x;
-  gy = (strip * p.stripStride + p.stripFirst) * p.stripRows + (y - strip * p.stripRows);
-  dst = (y * p.cam.W + x) * p.spp + k;
-  si = (int)(k / (uint32_t)p.cam.nIter);
-  sj = (int)(k - (uint32_t)si * (uint32_t)p.cam.nIter);
-  return true;
+/* ---- Work order -------------------------------------------------------------------------------------
+ * A sample is a chain of dependent queries — a few for most samples, 30-130 for the ones that go through
+ * refracting spheres — and a pass costs the same however few lanes it serves.  Handing the tiles out in
+ * scanline order ends every launch on a few warps working off the deep samples they happened to start last
+ * (8-10 ms per launch at 1 024 spheres: a tenth of a GPU's share of an 8K frame on eight GPUs).  So the queue
+ * head hands out only every tile's FIRST group (sample 0, or the first pixel sub-lattice at 1 spp: a quarter
+ * of the frame at most), the chain lengths of those samples classify the tile, and its remaining groups go
+ * into one of RT_ORDER_CLASSES buckets that are drained deepest class first:
+ *   - a first-group sample that reaches RT_DEEP_AT queries puts its tile into bucket 0 at once;
+ *   - otherwise the tile is classified when all 32 items of its first group have finished.
+ * Buckets are multi-producer / multi-consumer arrays in global memory (tail and head counters, entries
+ * written after the tail has moved: a consumer waits for the entry it has claimed).  A warp that finds the
+ * queue head exhausted and the buckets empty carries on with what it has in flight; the launch is over when
+ * every entry has been handed out and worked off.  The frame does not depend on the order (samples are
+ * independent, main.cpp:439). */
+__device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+
+__device__ __noinline__ void bucket_push(const TraceParams& p, uint32_t tile, uint32_t cls) {
+  for (uint32_t blk = 0; blk < p.nBlocks; ++blk) {
+    const unsigned pos = atomicAdd(&p.bucketCtl[cls], 1u);
+    atomicExch(&p.bucketEntries[(size_t)cls * p.nEntries + pos], tile * p.nBlocks + blk + 1u);
+  }
+}
+/* one first-group item is finished (count = its chain length; 0 for an item outside the frame) */
+__device__ __noinline__ void first_group_done(const TraceParams& p, uint32_t tile, uint32_t count) {
+  if (count > 1u) atomicMax(&p.tileMax[tile], count);
+  if (atomicAdd(&p.tileDone[tile], 1u) + 1u == 32u && atomicExch(&p.tilePushed[tile], 1u) == 0u) {
+    const unsigned mx = ld_volatile(&p.tileMax[tile]);      /* a late atomicMax of another lane only costs order quality */
+    bucket_push(p, tile, order_class(mx > count ? mx : count));
+  }
+}
+__device__ __noinline__ void first_group_deep(const TraceParams& p, uint32_t tile) {
+  if (atomicExch(&p.tilePushed[tile], 1u) == 0u) bucket_push(p, tile, 0u);
+}
+/* next entry of the deepest non-empty bucket, or RT_NONE.  *allOut = every entry of the frame has been handed out. */
+__device__ __noinline__ uint32_t bucket_pop(const TraceParams& p, bool* allOut) {
+  for (uint32_t cls = 0; cls < RT_ORDER_CLASSES; ++cls) {
+    for (;;) {
+      const unsigned h = ld_volatile(&p.bucketCtl[8 + cls]), t = ld_volatile(&p.bucketCtl[cls]);
+      if (h >= t) break;
+      if (atomicCAS(&p.bucketCtl[8 + cls], h, h + 1u) == h) {
+        unsigned e;
+        while ((e = ld_volatile(&p.bucketEntries[(size_t)cls * p.nEntries + h])) == 0u) { }
+        atomicAdd(&p.bucketCtl[16], 1u);
+        *allOut = false;
+        return e - 1u;
+      }
+    }
+  }
+  *allOut = ld_volatile(&p.bucketCtl[16]) >= p.nEntries;
+  return RT_NONE;
 }
 
 /* ---- slot storage: the 21-word records of rt_core.cuh (slot_pack / slot_unpack), either interleaved in
@@ -253,8 +298,6 @@ __host__ __device__ constexpr unsigned mask_of_sub(int sub) {
  * predicates / the constant bank on every trip, which costs issue slots in the hot loops) */
 __device__ __forceinline__ unsigned pin(unsigned v) { asm volatile("" : "+r"(v)); return v; }
 
-#define RT_FULL 0xFFFFFFFFu
-#define RT_NONE 0xFFFFFFFFu
 
 /* Append the flagged tests of one group to the lane's list; returns the bits that did not fit. */
 template <int ND, int G>
@@ -446,7 +489,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const ConstRec
       }
     } else {
       const uint32_t hdr = st.at(s0, W_HDR);
-      const int nd = (int)((hdr >> 2) & 7u), light = (int)(hdr >> 10);
+      const int nd = (int)((hdr >> 2) & 7u), light = (int)((hdr >> 10) & 0x7FFFu);
 #pragma unroll
       for (int k = 0; k < ND; ++k) {
         if (k < nd) {
@@ -745,7 +788,7 @@ __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx&
       }
     } else {
       const uint32_t hdr = st.at(s0, W_HDR);
-      const int nd = (int)((hdr >> 2) & 7u), light = (int)(hdr >> 10);
+      const int nd = (int)((hdr >> 2) & 7u), light = (int)((hdr >> 10) & 0x7FFFu);
 #pragma unroll
       for (int k = 0; k < ND; ++k) {
         if (k < nd) {
@@ -903,6 +946,11 @@ __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, const St&
   s.minT = ans.t; s.hitIdx = ans.h; s.blocked = ans.blocked;
   done = advance(s, stack, ctr, p.sc, p.cam, sg);
 #endif
+  if (s.first) {
+    /* the chain lengths of a tile's first group order its other groups (see "Work order") */
+    if (done) first_group_done(p, tile_of_dst(p.wm, s.pixel), (uint32_t)s.count);
+    else if (s.count == RT_DEEP_AT) first_group_deep(p, tile_of_dst(p.wm, s.pixel));
+  }
   if (done) {
     const V3 v = sample_value(s, p.cam);
     if (p.spp == 1u) {
@@ -923,159 +971,6 @@ __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, const St&
     store_slot(st, sv, s);
   }
   return (uint32_t)s.kind | ((uint32_t)s.ndirs << 4);
-}
-
-/* Drain balancing.  Once the tile queue is dry a lane's slots are no longer refilled, and a pass costs the
- * same however few lanes it serves: the warp would run until its BUSIEST lane has worked off its slots
- * one or two queries at a time.  Instead, whenever two lanes' live-slot counts differ by two or more, the
- * fullest lanes hand one slot each (21-word record + its suspended frames + its census byte) to the
- * emptiest lanes through shuffles, so the warp's passes stay full until it holds fewer queries than lanes.
- * Samples are independent (main.cpp:439) and carry their result index, so any lane may finish them. */
-template <int NSLOTS, class St>
-__device__ __forceinline__ void rebalance(const St& st, Frame* stacks, uint32_t& tags, uint32_t lane, uint32_t& migrated) {
-#pragma unroll 1
-  for (int round = 0; round < NSLOTS; ++round) {
-    int live = 0, ks = -1, kr = -1;
-#pragma unroll
-    for (int k = 0; k < NSLOTS; ++k) {
-      const bool lv = ((tags >> (8 * k)) & 0xFu) != (uint32_t)K_NULL;
-      live += lv ? 1 : 0;
-      if (lv) ks = k; else if (kr < 0) kr = k;      /* a donor gives its last live slot, a receiver fills its first free one */
-    }
-    const int mx = __reduce_max_sync(RT_FULL, live), mn = __reduce_min_sync(RT_FULL, live);
-    if (mx - mn < 2) return;
-    const unsigned dmask = __ballot_sync(RT_FULL, live == mx), rmask = __ballot_sync(RT_FULL, live == mn);
-    const int npairs = min(__popc(dmask), __popc(rmask));
-    const unsigned lt = (1u << lane) - 1u;
-    const int rankD = __popc(dmask & lt), rankR = __popc(rmask & lt);
-    const bool isD = (live == mx) && rankD < npairs, isR = (live == mn) && rankR < npairs;
-    int partner = (int)lane;
-    if (isR) partner = (int)__fns(dmask, 0, rankR + 1);      /* the rankR-th donor */
-    if (isD) partner = (int)__fns(rmask, 0, rankD + 1);
-    const int nfD = isD ? (int)((st.at(ks, W_HDR) >> 5) & 31u) : 0;      /* frames in use = top + 1 */
-#pragma unroll 1
-    for (int wd = 0; wd < RT_SLOT_WORDS; ++wd) {
-      uint32_t v = isD ? st.at(ks, wd) : 0u;
-      v = __shfl_sync(RT_FULL, v, partner);
-      if (isR) st.at(kr, wd) = v;
-    }
-    const int nf = __shfl_sync(RT_FULL, nfD, partner);
-    const int nfMax = __reduce_max_sync(RT_FULL, nfD);
-    uint32_t* fw = reinterpret_cast<uint32_t*>(stacks);
-    constexpr int FW = (int)(sizeof(Frame) / sizeof(uint32_t));
-#pragma unroll 1
-    for (int f = 0; f < nfMax; ++f) {
-#pragma unroll 1
-      for (int wd = 0; wd < FW; ++wd) {
-        uint32_t v = (isD && f < nfD) ? fw[(ks * RT_MAX_STACK + f) * FW + wd] : 0u;
-        v = __shfl_sync(RT_FULL, v, partner);
-        if (isR && f < nf) fw[(kr * RT_MAX_STACK + f) * FW + wd] = v;
-      }
-    }
-    const uint32_t tgD = isD ? ((tags >> (8 * ks)) & 0xFFu) : 0u;
-    const uint32_t tg = __shfl_sync(RT_FULL, tgD, partner);
-    if (isR) { tags = (tags & ~(0xFFu << (8 * kr))) | (tg << (8 * kr)); ++migrated; }
-    if (isD) {
-      tags &= ~(0xFFu << (8 * ks));
-      st.at(ks, W_PIXEL) = RT_NO_PIXEL;
-      st.at(ks, W_HDR) = 0u;
-    }
-  }
-}
-
-/* Sparse rounds (the end of a warp's drain).  A sample is a chain of up to several hundred dependent
- * queries (a depth-8 tree has up to 255 calls of three queries each), and a normal pass costs the full
- * sphere loop however few queries it serves: the last samples of a launch would keep an almost empty SM
- * busy for milliseconds.  Once a warp holds only a handful of queries it serves them ONE AT A TIME with
- * the spheres spread over the lanes: lane l filters spheres l, l+32, ..., puts its own candidates through
- * the reference's exact expressions, and a warp reduction picks the answer (closest hit with the first
- * index winning ties, occlusion bits, first container).  Same arithmetic per (query, sphere) pair as the
- * passes, so the answers — and the frame — are bit-identical. */
-template <bool USE_CONST, bool ACCEL, class St>
-__device__ __forceinline__ void sparse_query(const TraceParams& p, const ConstRecords& cr, const WarpCtx& w, const St& st,
-                                             int owner, int ks, uint32_t lane, Counters& ctr, Answer& ans, ShadowGeo& sg) {
-  /* the per-sphere filter records: staged copy, or (accelerated mode: only the cluster form is staged) global memory */
-  auto rec = [&](uint32_t i) { return ACCEL ? p.sc.filt[i] : load_filt<USE_CONST>(w, cr, i); };
-  /* the owner's record header and geometry, broadcast */
-  const bool mine = (int)lane == owner;
-  const uint32_t hdr = __shfl_sync(RT_FULL, mine ? st.at(ks, W_HDR) : 0u, owner);
-  const int kind = (int)(hdr & 3u), nd = (int)((hdr >> 2) & 7u), light = (int)(hdr >> 10);
-  V3 P = mine ? st.ldv(ks, W_P) : mk(0.f, 0.f, 0.f), d = mine ? st.ldv(ks, W_RAYD) : mk(0.f, 0.f, 0.f);
-  P.x = __shfl_sync(RT_FULL, P.x, owner); P.y = __shfl_sync(RT_FULL, P.y, owner); P.z = __shfl_sync(RT_FULL, P.z, owner);
-  d.x = __shfl_sync(RT_FULL, d.x, owner); d.y = __shfl_sync(RT_FULL, d.y, owner); d.z = __shfl_sync(RT_FULL, d.z, owner);
-  const uint32_t n = p.sc.n, nPad = p.sc.nPad;
-  ans.t = 1000.f; ans.h = -1; ans.blocked = 0u;
-  if (kind == K_TRACE) {
-    const OriginQ O = make_origin(P);
-    DirQ D;
-    if (make_dir_fast(D, P, d)) {                       /* zero direction: certain miss, no loop */
-      const bool exact = p.noFilter || !(origin_filterable(O) && dir_filterable(D));
-      float bt = 1000.f; uint32_t bi = 0x3FFFu;
-      for (uint32_t i = lane; i < nPad; i += 32u) {
-        bool cand = exact;
-        if (!exact) { const float4_ f = rec(i); cand = !(filter_ray(O, D, filter_ch(O, f), f) < 0.f); }
-        if (cand && i < n) {
-          ctr.exactTests++;
-          const float t = ray_sphere_t(p.sc.geo[i], P, d);
-          if (t > 0.f && t < bt) { bt = t; bi = i; }      /* increasing i per lane: strict < keeps the first index */
-        }
-      }
-      /* warp minimum of (t, index): positive floats order like their bit patterns */
-      unsigned long long key = ((unsigned long long)__float_as_uint(bt) << 32) | bi;
-#pragma unroll
-      for (int o = 16; o > 0; o >>= 1) { const unsigned long long k2 = __shfl_xor_sync(RT_FULL, key, o); key = k2 < key ? k2 : key; }
-      const float t = __uint_as_float((unsigned)(key >> 32));
-      if (t < 1000.f) { ans.t = t; ans.h = (int)(unsigned)(key & 0xFFFFFFFFu); }
-    }
-  } else if (kind == K_SHADOW) {
-    const OriginQ O = make_origin(P);
-    const bool ofil = origin_filterable(O);
-    DirQ D[RT_SHADOW_BATCH];
-    unsigned exact = 0u, blocked = 0u;
-#pragma unroll
-    for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
-      sg.d[k] = mk(0.f, 0.f, 0.f); sg.gap[k] = 0.f;
-      D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f;
-      if (k < nd) {
-        const float4_ lp = p.sc.lpos[light + k];
-        const V3 dir = vsub(mk(lp.x, lp.y, lp.z), P);       /* raytracer.h:279-286 */
-        sg.gap[k] = vdot(dir, dir);
-        sg.d[k] = vunit_i(dir);
-        make_dir_unit(D[k], P, sg.d[k]);
-        if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
-      }
-    }
-    for (uint32_t i = lane; i < nPad; i += 32u) {
-      const float4_ f = rec(i);
-      const float ch = filter_ch(O, f);
-#pragma unroll
-      for (int k = 0; k < RT_SHADOW_BATCH; ++k) {
-        if (k < nd && !((blocked >> k) & 1u) && i < n) {
-          const bool cand = ((exact >> k) & 1u) || !(filter_ray(O, D[k], ch, f) < 0.f);
-          if (cand) {
-            ctr.exactTests++;
-            if (resolve_shadow(P, sg.d[k], sg.gap[k], p.sc.geo[i])) blocked |= 1u << k;
-          }
-        }
-      }
-    }
-    ans.blocked = __reduce_or_sync(RT_FULL, blocked);
-  } else {   /* K_CONTAIN: the probe point of raytracer.h:688-692 */
-    const V3 q = vadd(vscale(0.01f, d), P);
-    const OriginQ O = make_origin(q);
-    const bool exact = p.noFilter || !origin_filterable(O);
-    unsigned first = 0xFFFFFFFFu;
-    for (uint32_t i = lane; i < nPad && first == 0xFFFFFFFFu; i += 32u) {
-      bool cand = exact;
-      if (!exact) { const float4_ f = rec(i); cand = !(filter_point(O, filter_ch(O, f)) < 0.f); }
-      if (cand && i < n) {
-        ctr.exactTests++;
-        if (contains_exact(p.sc.geo[i], q)) first = i;     /* increasing i per lane: this lane's first container */
-      }
-    }
-    first = __reduce_min_sync(RT_FULL, first);
-    ans.h = (first == 0xFFFFFFFFu) ? -1 : (int)first;
-  }
 }
 
 template <bool USE_CONST, int NSLOTS, bool ACCEL, bool SMEM_SLOTS>
@@ -1137,54 +1032,84 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   float laneMax = 0.f;
   uint32_t passT = 0, passS4 = 0, passC = 0;                /* passes by kind (warp-uniform) */
   uint32_t servedT = 0, servedS = 0, servedC = 0;            /* sub-queries of this lane served */
-  uint32_t migrated = 0;                                     /* slots this lane received from busier lanes */
 
-  uint32_t wbase = 0, wend = 0;          /* warp-uniform slice of the tile queue */
-  bool queueDry = false;
+  uint32_t wbase = 0, wend = 0;          /* warp-uniform slice of work: items wbase..wend-1 of the queue head or of a bucket entry */
+  uint32_t segTile = 0, segK0 = 0;       /* bucket entry: its tile and first group */
+  bool segBucket = false, headDry = false;
+  bool queueDry = false;                 /* nothing left to hand out: the warp finishes what it has in flight */
+#if RT_LOCKSTEP
+  __shared__ unsigned sVote[RT_BLOCK / 32 / RT_LOCK_WARPS][3][8];       /* a group's census of a round: nT, nS, nC, ndMax, warps not finished */
+  if (tid < (RT_BLOCK / 32 / RT_LOCK_WARPS) * 24) (&sVote[0][0][0])[tid] = 0u;
+  __syncthreads();
+  int voteBuf = 0;
+#endif
 
   for (;;) {
     /* ---- refill ---- */
+    bool starved = false;      /* the queue head is exhausted and the buckets are empty, but entries are still to come */
 #pragma unroll 1
-    for (int k = 0; k < NSLOTS && !queueDry; ++k) {
+    for (int k = 0; k < NSLOTS && !queueDry && !starved; ++k) {
       bool need = (((tags >> (8 * k)) & 0xFu) == (uint32_t)K_NULL);
-      while (!queueDry) {
+      while (!queueDry && !starved) {
         const unsigned m = __ballot_sync(RT_FULL, need);
         if (m == 0) break;
         if (wbase >= wend) {
-          uint32_t b = 0;
-          if (lane == 0) b = atomicAdd(p.workCounter, p.chunk);
-          b = __shfl_sync(RT_FULL, b, 0);
-          if (b >= p.totalWork) {
-            queueDry = true;
-#ifdef RT_PHASE_TIMING
-            w.tDry = clock64();
-#endif
-            break;
+          /* next slice of work (warp-uniform): the queue head first, then the buckets (see "Work order") */
+          if (!headDry) {
+            uint32_t b = 0;
+            if (lane == 0) b = atomicAdd(p.workCounter, p.chunk);
+            b = __shfl_sync(RT_FULL, b, 0);
+            if (b >= p.total1) headDry = true;
+            else { wbase = b; wend = (b + p.chunk < p.total1) ? b + p.chunk : p.total1; segBucket = false; }
           }
-          wbase = b;
-          wend = (b + p.chunk < p.totalWork) ? b + p.chunk : p.totalWork;
+          if (headDry && wbase >= wend) {
+            uint32_t e = RT_NONE;
+            bool allOut = true;
+            if (p.lpt && lane == 0) e = bucket_pop(p, &allOut);
+            e = __shfl_sync(RT_FULL, e, 0);
+            allOut = __shfl_sync(RT_FULL, (int)allOut, 0) != 0;
+            if (e == RT_NONE) {
+              if (allOut) {
+                queueDry = true;
+#ifdef RT_PHASE_TIMING
+                w.tDry = clock64();
+#endif
+              } else starved = true;
+              break;
+            }
+            segTile = e / p.nBlocks;
+            segK0 = 1u + (e - segTile * p.nBlocks) * p.kPerBlock;
+            const uint32_t kc = (p.wm.K - segK0 < p.kPerBlock) ? p.wm.K - segK0 : p.kPerBlock;
+            wbase = 0; wend = 32u * kc; segBucket = true;
+          }
         }
         const uint32_t avail = wend - wbase;
         const uint32_t rank = __popc(m & ((1u << lane) - 1u));
         if (need && rank < avail) {
+          const uint32_t idx = wbase + rank, grp = idx >> 5;
+          uint32_t tile, kk;
+          if (segBucket) { tile = segTile; kk = segK0 + grp; }
+          else if (p.lpt) { tile = grp; kk = 0u; }
+          else { tile = grp / p.wm.K; kk = grp - tile * p.wm.K; }
           uint32_t gx, gy, dst;
           int si, sj;
-          if (work_to_task(p, wbase + rank, gx, gy, dst, si, sj)) {
+          if (work_item(p.wm, tile, kk, idx & 31u, gx, gy, dst, si, sj)) {
             Slot s;
             s.obj = 0; s.light = 0;
             s.P = s.Nrm = s.lit = mk(0.f, 0.f, 0.f);
             start_task(s, ctr, p.cam, gx, gy, dst, si, sj);
+            s.first = (p.lpt && kk == 0u) ? 1 : 0;
             store_slot(st, k, s);
             need = false;
             tags = (tags & ~(0xFFu << (8 * k))) | (((uint32_t)K_TRACE | (1u << 4)) << (8 * k));
+          } else if (p.lpt && kk == 0u) {
+            first_group_done(p, tile, 0u);        /* an item outside the frame still counts towards the tile's 32 */
           }
         }
         const uint32_t cnt = __popc(m);
         wbase += (cnt < avail) ? cnt : avail;
       }
     }
-
-    if (queueDry && p.rebalance) rebalance<NSLOTS>(st, stacks, tags, lane, migrated);
 
     /* ---- vote ---- */
     int t0 = -1, t1 = -1, s0 = -1, c0 = -1, c1 = -1, nd = 0;
@@ -1199,16 +1124,52 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
     /* a shadow pass also takes one trace ray from lanes that have no shadow batch waiting */
     const int sOrT = (s0 >= 0) ? s0 : t0;
     const int ndS = (s0 >= 0) ? nd : (t0 >= 0 ? 1 : 0);
-    const unsigned nT = __reduce_add_sync(RT_FULL, (unsigned)((t0 >= 0) + (t1 >= 0)));
-    const unsigned nS = __reduce_add_sync(RT_FULL, (unsigned)ndS);
-    const unsigned nC = __reduce_add_sync(RT_FULL, (unsigned)((c0 >= 0) + (c1 >= 0)));
-    const int ndMax = __reduce_max_sync(RT_FULL, nd);
+    unsigned nT = __reduce_add_sync(RT_FULL, (unsigned)((t0 >= 0) + (t1 >= 0)));
+    unsigned nS = __reduce_add_sync(RT_FULL, (unsigned)ndS);
+    unsigned nC = __reduce_add_sync(RT_FULL, (unsigned)((c0 >= 0) + (c1 >= 0)));
+    int ndMax = __reduce_max_sync(RT_FULL, nd);
+#if RT_LOCKSTEP
+    /* Lockstep passes: the warps of a GROUP (RT_LOCK_WARPS warps of the CTA) start every pass together (one named
+     * barrier per pass), so that at any time a group executes one phase of a pass — the instruction working set of an
+     * SM is a few phases instead of sixteen (the kernel is ~75 KB of code against a 32 KB instruction cache; ncu: 44 %
+     * of the warp samples at 256 spheres are instruction-fetch stalls without it, 3 % with it).
+     * RT_LOCKSTEP 1: the group also votes together (equal loop lengths; a warp with nothing of the group's kind sits
+     * the pass out); 2: every warp keeps its own vote. */
+    {
+      const unsigned grp = (tid >> 5) / RT_LOCK_WARPS;
+      unsigned* vt = sVote[grp][voteBuf];
+      const bool idle = (nT | nS | nC) == 0u;
+      if (lane == 0) {
+#if RT_LOCKSTEP == 1
+        if (nT) atomicAdd(&vt[0], nT);
+        if (nS) atomicAdd(&vt[1], nS);
+        if (nC) atomicAdd(&vt[2], nC);
+        if (ndMax) atomicMax(&vt[3], (unsigned)ndMax);
+#endif
+        if (!(idle && queueDry)) atomicAdd(&vt[4], 1u);
+      }
+      asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "r"(32u * RT_LOCK_WARPS) : "memory");
+      const unsigned cT = vt[0], cS = vt[1], cC = vt[2], cNd = vt[3], cLive = vt[4];
+      /* three buffers in rotation: clear the PREVIOUS round's (every read of it came before the barrier above, its
+       * next use comes after the next barrier) */
+      if ((tid & (32u * RT_LOCK_WARPS - 1u)) < 5u) sVote[grp][(voteBuf + 2) % 3][tid & 7u] = 0u;
+      voteBuf = (voteBuf + 1) % 3;
+      if (cLive == 0u) break;
+      if (idle && starved) __nanosleep(200);
+#if RT_LOCKSTEP == 1
+      if ((cT | cS | cC) == 0u) continue;
+      nT = cT; nS = cS; nC = cC; ndMax = (int)cNd;
+#else
+      if (idle) continue;
+#endif
+    }
+#else
     if ((nT | nS | nC) == 0u) {
       if (queueDry) break;
+      if (starved) __nanosleep(200);
       continue;
     }
-    /* the last few queries of this warp are served one at a time, lane-parallel over the spheres */
-    if (queueDry && p.sparseBelow && nT + nC + __popc(__ballot_sync(RT_FULL, s0 >= 0)) <= p.sparseBelow) break;
+#endif
     /* serve the kind that fills the largest share of its pass: capacity 64 sub-queries for
      * trace / contain passes, 32 x (2 or 4) for a shadow pass (scenes with <= 2 lights fill half of it) */
     const unsigned capS = (ndMax <= 2) ? 64u : 128u;
@@ -1217,6 +1178,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
                      : (nT >= nC) ? K_TRACE : K_CONTAIN;
     const int sv0 = (mode == K_SHADOW) ? sOrT : (mode == K_TRACE) ? t0 : c0;
     const int sv1 = (mode == K_SHADOW) ? -1 : (mode == K_TRACE) ? t1 : c1;
+#if RT_LOCKSTEP == 1
+    if (!__any_sync(RT_FULL, sv0 >= 0)) continue;      /* nothing of the group's kind in this warp */
+#endif
     Answer a0, a1;
     a0.t = a1.t = 1000.f; a0.h = a1.h = -1; a0.blocked = a1.blocked = 0u;
     ShadowGeo sg;
@@ -1250,32 +1214,6 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
     RT_TICK(4);
   }
 
-  /* ---- sparse drain: whatever is still pending in this warp, one query at a time ---- */
-  uint32_t sparseQ = 0;
-  {
-    for (;;) {
-      int ks = -1;
-#pragma unroll
-      for (int k = NSLOTS - 1; k >= 0; --k)
-        if (((tags >> (8 * k)) & 0xFu) != (uint32_t)K_NULL) ks = k;
-      const unsigned m = __ballot_sync(RT_FULL, ks >= 0);
-      if (m == 0u) break;
-      const int owner = __ffs((int)m) - 1;
-      const int oks = __shfl_sync(RT_FULL, ks, owner);
-      Answer a;
-      ShadowGeo sg;
-      sparse_query<USE_CONST, ACCEL>(p, cr, w, st, owner, (int)lane == owner ? ks : oks, lane, ctr, a, sg);
-      const int sv = ((int)lane == owner) ? ks : -1;
-      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * RT_MAX_STACK], ctr, laneMax, &sg, a);
-      if (sv >= 0) {
-        const uint32_t old = (tags >> (8 * sv)) & 0xFFu;
-        const uint32_t subs = ((old & 0xFu) == (uint32_t)K_SHADOW) ? (old >> 4) : 1u;
-        if ((old & 0xFu) == (uint32_t)K_TRACE) servedT += subs; else if ((old & 0xFu) == (uint32_t)K_SHADOW) servedS += subs; else servedC += subs;
-        sparseQ += subs;
-        tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
-      }
-    }
-  }
 #ifdef RT_PHASE_TIMING
   if (lane == 0)
   {
@@ -1287,22 +1225,19 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   /* ---- per-warp reductions ---- */
   unsigned mb = __float_as_uint(laneMax);   /* laneMax >= 0: uint order == float order */
   mb = __reduce_max_sync(RT_FULL, mb);
-  unsigned long long v[12];
+  unsigned long long v[10];
   v[0] = ctr.rays; v[1] = ctr.shadow; v[2] = ctr.containQ; v[3] = ctr.containT;
   v[4] = ctr.exactTests; v[5] = ctr.samples; v[6] = ctr.nullRays;
-  v[7] = servedT; v[8] = servedS; v[9] = servedC; v[10] = sparseQ; v[11] = migrated;
+  v[7] = servedT; v[8] = servedS; v[9] = servedC;
 #pragma unroll
-  for (int i = 0; i < 12; ++i)
+  for (int i = 0; i < 10; ++i)
     for (int o = 16; o > 0; o >>= 1) v[i] += __shfl_xor_sync(RT_FULL, v[i], o);
   if (lane == 0) {
     if (mb) atomicMax(p.maxBits, mb);
 #pragma unroll
     for (int i = 0; i < 10; ++i) atomicAdd(&p.counters[i], v[i]);
-    atomicAdd(&p.counters[22], v[10]);
-    atomicAdd(&p.counters[23], v[11]);
-    /* sub-query capacity offered by this warp's passes (32 lanes x 2, or x 4 for a shadow pass; a sparse round
-     * offers exactly the query it serves) */
-    atomicAdd(&p.counters[10], 64ull * passT + 128ull * passS4 + 64ull * passC + v[10]);
+    /* sub-query capacity offered by this warp's passes (32 lanes x 2, or x 4 for a shadow pass) */
+    atomicAdd(&p.counters[10], 64ull * passT + 128ull * passS4 + 64ull * passC);
     atomicAdd(&p.counters[11], 1ull * passT + 1ull * passS4 + 1ull * passC);
     atomicAdd(&p.counters[12], (unsigned long long)passT);
     atomicAdd(&p.counters[14], (unsigned long long)passS4);

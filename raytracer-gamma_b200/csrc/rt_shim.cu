@@ -19,6 +19,7 @@ using namespace rtg;
 #ifndef RT_DEFAULT_SLOTS
 #define RT_DEFAULT_SLOTS 4
 #endif
+#define RT_K_PER_ENTRY 8u            /* groups of one tile per bucket entry (work order) */
 #define RT_COPY_CHUNK (8u << 20)     /* pageable readback: D2H and the host memcpy alternate over two pinned chunks */
 #define RT_FLUSH_BYTES (256u << 20)  /* rt_cuda_flush_l2: larger than the 126 MB L2 */
 
@@ -53,6 +54,7 @@ struct rt_cuda_ctx {
   unsigned char* dRgb8 = nullptr; size_t rgbCap = 0;
   unsigned int* dWork = nullptr;     /* [0] queue head, [1] max bits */
   unsigned long long* dCounters = nullptr;
+  unsigned int* dOrder = nullptr; size_t orderCap = 0;   /* work-order state of a launch (rt_kernels.cuh "Work order") */
   void* dFlush = nullptr;
 
   /* synchronous readback through two pinned chunks */
@@ -72,8 +74,7 @@ struct rt_cuda_ctx {
 
   /* options */
   int staging = 0, noFilter = 0, blocksPerSM = 0, slots = 0;
-  int rebalance = 1;               /* drain balancing (rt_kernels.cuh rebalance) */
-  int sparseBelow = 12;            /* sparse rounds for the last queries of a warp (rt_kernels.cuh sparse_query) */
+  int order = 1;                   /* 1: longest chains first (default) | 0: tiles in scanline order */
   int slotMode = 0;                /* 0 auto | 1 slot records in shared memory | 2 in local memory */
   int accel = 0;                   /* 1: two-level cluster filter (optional accelerated mode) */
   uint32_t nc = 0, ncPad = 0;
@@ -175,7 +176,7 @@ extern "C" void rt_cuda_destroy(rt_cuda_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
   cudaFree(ctx->dScene); cudaFree(ctx->dFb); cudaFree(ctx->dPacked); cudaFree(ctx->dRgb8); cudaFree(ctx->dSamples);
-  cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->dFlush);
+  cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->dFlush); cudaFree(ctx->dOrder);
   for (int i = 0; i < 2; ++i) {
     if (ctx->hChunk[i]) cudaFreeHost(ctx->hChunk[i]);
     if (ctx->evChunk[i]) cudaEventDestroy(ctx->evChunk[i]);
@@ -219,8 +220,7 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
   if (!strcmp(key, "accel")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->accel = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "rebalance")) { ctx->rebalance = value ? 1 : 0; return RT_CUDA_OK; }
-  if (!strcmp(key, "sparse_below")) { if (value < 0 || value > 64) return RT_CUDA_ERR_INVALID_ARG; ctx->sparseBelow = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "order")) { ctx->order = value ? 1 : 0; return RT_CUDA_OK; }
   if (!strcmp(key, "slot_mode")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->slotMode = (int)value; return RT_CUDA_OK; }
 #ifdef RT_DEV_VARIANTS   /* development builds only: slot-count variants of the local-memory kernel */
   if (!strcmp(key, "slots")) { if (value != 0 && (value < 3 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->slots = (int)value; return RT_CUDA_OK; }
@@ -309,10 +309,16 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   p.cam = make_camera(width, height, zoom, aliasFactor, maxStack, (int)ctx->n);
   if (p.cam.nIter >= (1 << 20)) return RT_CUDA_ERR_TOO_LARGE;          /* make_camera's cap: alias too large to iterate */
   const uint64_t spp64 = (uint64_t)p.cam.nIter * (uint64_t)p.cam.nIter;
-  p.tilesX = (width + 7u) / 8u;
-  const uint32_t tilesY = (localRows + 3u) / 4u;
-  if (spp64 >= (1ull << 32) || (uint64_t)p.tilesX * tilesY * 32u * spp64 >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
+  if (spp64 >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
   const uint32_t spp = (uint32_t)spp64;
+  p.wm = make_workmap(width, localRows, stripRows, stripFirst, stripStride, spp, (uint32_t)p.cam.nIter);
+  if ((uint64_t)p.wm.tilesX * p.wm.tilesY * 32u * p.wm.K >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
+  /* work order: every tile's first group from the queue head, the other groups deepest tiles first (rt_kernels.cuh
+   * "Work order"); bucket entries cover RT_K_PER_ENTRY groups of one tile */
+  const bool lpt = ctx->order != 0 && p.wm.K > 1u;
+  const uint32_t nBlocks = (p.wm.K - 1u + RT_K_PER_ENTRY - 1u) / RT_K_PER_ENTRY;
+  const uint64_t nEntries64 = (uint64_t)p.wm.nTiles * nBlocks;
+  if (nEntries64 >= (1ull << 31)) return RT_CUDA_ERR_TOO_LARGE;
 
   /* the accelerated mode needs something to cull, its records in shared memory, and the cluster form */
   const size_t listBytes = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short);
@@ -368,7 +374,7 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
     CU(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&perSM, kfn, RT_BLOCK, smem));
     if (perSM < 1) return RT_CUDA_ERR_TOO_LARGE;
     if (ctx->blocksPerSM > 0 && ctx->blocksPerSM < perSM) perSM = ctx->blocksPerSM;
-    totalWork = p.tilesX * tilesY * 32u * spp;
+    totalWork = p.wm.nTiles * 32u * p.wm.K;
     grid = (uint32_t)ctx->smCount * (uint32_t)perSM;
     const uint32_t needBlocks = (totalWork + RT_BLOCK - 1) / RT_BLOCK;
     if (grid > needBlocks) grid = needBlocks;
@@ -376,6 +382,11 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   }
   int rc = ensure_dev(ctx, ctx->dFb, ctx->fbCap, pixels ? pixels : 1);
   if (rc) { ctx->haveFrame = false; return rc; }
+  const size_t words = 32 + 3 * (size_t)p.wm.nTiles + (size_t)RT_ORDER_CLASSES * (size_t)nEntries64;
+  if (lpt && pixels) {
+    rc = ensure_dev(ctx, ctx->dOrder, ctx->orderCap, words);
+    if (rc) { ctx->haveFrame = false; return rc; }
+  }
   if (spp > 1 && pixels) {
     rc = ensure_dev(ctx, ctx->dSamples, ctx->samplesCap, pixels * spp);
     if (rc) { ctx->haveFrame = false; return rc; }
@@ -402,18 +413,26 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   p.workCounter = ctx->dWork;
   p.maxBits = ctx->dWork + 1;
   p.counters = ctx->dCounters;
-  p.localRows = localRows;
-  p.stripRows = stripRows; p.stripFirst = stripFirst; p.stripStride = stripStride;
-  p.totalWork = totalWork;
+  p.lpt = lpt ? 1u : 0u;
+  p.total1 = lpt ? p.wm.nTiles * 32u : totalWork;
+  p.kPerBlock = RT_K_PER_ENTRY; p.nBlocks = nBlocks; p.nEntries = (uint32_t)nEntries64;
+  p.tileMax = p.tileDone = p.tilePushed = p.bucketEntries = p.bucketCtl = nullptr;
+  if (lpt) {
+    /* one zeroed allocation: bucket control (32 words) | tileMax | tileDone | tilePushed | entries[classes][nEntries] */
+    CU(cudaMemsetAsync(ctx->dOrder, 0, words * sizeof(unsigned int), ctx->stream));
+    p.bucketCtl = ctx->dOrder;
+    p.tileMax = ctx->dOrder + 32;
+    p.tileDone = p.tileMax + p.wm.nTiles;
+    p.tilePushed = p.tileDone + p.wm.nTiles;
+    p.bucketEntries = p.tilePushed + p.wm.nTiles;
+  }
   p.spp = spp;
   p.samples = (spp > 1) ? ctx->dSamples : nullptr;
   p.noFilter = ctx->noFilter;
-  p.rebalance = ctx->rebalance;
-  p.sparseBelow = (uint32_t)ctx->sparseBelow;
   p.list1Max = list1Max;
   /* queue granule: small enough to balance the tail, large enough to amortise the atomic */
   const uint32_t warps = grid * (RT_BLOCK / 32);
-  uint32_t chunk = (totalWork / (warps * 16u)) & ~31u;
+  uint32_t chunk = (p.total1 / (warps * 16u)) & ~31u;
   if (chunk < 32u) chunk = 32u;
   if (chunk > 256u) chunk = 256u;
   p.chunk = chunk;
@@ -643,7 +662,6 @@ extern "C" int rt_cuda_get_stats(rt_cuda_ctx* ctx, rt_cuda_stats* out) {
   s.served_trace = c[7]; s.served_shadow = c[8]; s.served_contain = c[9]; s.passes = c[11];
   s.passes_trace = c[12]; s.passes_shadow2 = c[13]; s.passes_shadow4 = c[14]; s.passes_contain = c[15];
   for (int i = 0; i < 6; ++i) s.phase_cycles[i] = c[16 + i];
-  s.sparse_queries = c[22]; s.migrated_slots = (uint32_t)c[23];
   s.filter_tests = ctx->noFilter ? 0 : c[10] * (unsigned long long)(s.accel ? ctx->ncPad : ctx->nPad);   /* accelerated mode: cluster tests only */
   s.sph_num = ctx->n; s.sph_padded = ctx->nPad; s.lgt_num = ctx->nl;
   s.width = ctx->W; s.height = ctx->H; s.local_rows = ctx->localRows;

@@ -20,6 +20,7 @@ ap.add_argument("--cubin")
 ap.add_argument("--flags", default="")
 ap.add_argument("--kernel", default=None, help="regex on the mangled kernel name (default: taken from the capture)")
 ap.add_argument("--lines", type=int, default=0, help="also print the N hottest source lines")
+ap.add_argument("--stalls", action="store_true", help="per phase: the stall reasons of its samples")
 ap.add_argument("--root", default=None, help="source tree of the captured build (default: this checkout)")
 args = ap.parse_args()
 if args.root:
@@ -168,11 +169,18 @@ def classify(frames, sub):
     inner = [(f, l) for f, l, fn in fns if fn == "trace_body"]
     return kernel_phase(inner[-1][1]) if inner else "kernel: other"
 
+STALLS = ["stall_no_inst", "stall_long_sb", "stall_wait", "stall_math", "stall_not_selected", "stall_selected", "stall_branch_resolving",
+          "stall_short_sb", "stall_dispatch", "stall_lg", "stall_mio", "stall_barrier"]
+stall = collections.defaultdict(collections.Counter)
 inst = collections.Counter(); samp = collections.Counter(); thr = collections.Counter(); byline = collections.Counter(); static = collections.Counter()
 ti = ts = 0
 for r, (frames, sub) in zip(data, insts):
     a, b, t = (1, 1, 32) if STATIC else (int(r[ix["Instructions Executed"]]), int(r[ix["# Samples"]]), int(r[ix["Thread Instructions Executed"]]))
     key = classify(frames, sub)
+    if not STATIC and args.stalls:
+        for sname in STALLS:
+            if sname in ix and r[ix[sname]]:
+                stall[key][sname] += int(r[ix[sname]])
     inst[key] += a; samp[key] += b; thr[key] += t; ti += a; ts += b; static[key] += 1
     if frames:
         byline[frames[-1] if frames[-1][0] == "rt_kernels.cuh" else frames[0]] += b
@@ -183,6 +191,17 @@ for k, c in sorted(samp.items(), key=lambda kv: -kv[1]):
     if inst[k] == 0 and c == 0:
         continue
     print(f"{k:44s} {100 * inst[k] / ti:8.2f} {100 * c / ts:10.2f} {thr[k] / max(1, 32 * inst[k]):9.3f} {static[k]:6d}")
+if args.stalls and not STATIC:
+    print("stall reasons, % of ALL samples of the kernel (rows: phases; columns: " + " ".join(x[6:] for x in STALLS) + ")")
+    tot = collections.Counter()
+    for k, c in sorted(samp.items(), key=lambda kv: -kv[1]):
+        if c * 200 < ts:
+            continue
+        print(f"{k:44s} " + " ".join(f"{100 * stall[k][x] / ts:6.2f}" for x in STALLS))
+    for k in stall:
+        for x in STALLS:
+            tot[x] += stall[k][x]
+    print(f"{'TOTAL':44s} " + " ".join(f"{100 * tot[x] / ts:6.2f}" for x in STALLS))
 print(f"static SASS instructions {len(data)} ({len(data) * 16 / 1024:.1f} KB)")
 grp = collections.Counter(); grs = collections.Counter()
 for k in inst:

@@ -1,16 +1,29 @@
-"""Development aid: the handful of ncu raw-page metrics the roofline discussion uses.  usage: ncu_metrics.py X.ncu-rep [...]"""
+"""Development aid: the handful of ncu raw-page metrics the roofline discussion uses.
+usage: ncu_metrics.py X.ncu-rep|X.raw.csv [...]   (a .csv is the output of `ncu -i X.ncu-rep --page raw --csv`)"""
 import csv, subprocess, sys
 WANT = ['gpu__time_duration.sum', 'launch__registers_per_thread', 'launch__occupancy_limit_shared_mem', 'launch__occupancy_limit_registers',
-        'dram__bytes_read.sum', 'dram__bytes_write.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
+        'launch__shared_mem_per_block_dynamic', 'dram__bytes_read.sum', 'dram__bytes_write.sum', 'smsp__issue_active.avg.pct_of_peak_sustained_active',
         'sm__pipe_fma_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_fma.avg.pct_of_peak_sustained_active',
+        'sm__pipe_fmaheavy_cycles_active.avg.pct_of_peak_sustained_active', 'sm__inst_executed_pipe_alu.avg.pct_of_peak_sustained_active',
+        'sm__inst_executed_pipe_lsu.avg.pct_of_peak_sustained_active', 'sm__throughput.avg.pct_of_peak_sustained_elapsed',
         'l1tex__t_sector_hit_rate.pct', 'lts__t_sector_hit_rate.pct', 'smsp__thread_inst_executed_per_inst_executed.ratio',
         'sm__warps_active.avg.pct_of_peak_sustained_active', 'smsp__warps_eligible.avg.per_cycle_active', 'smsp__inst_executed.sum',
-        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum']
-for rep in sys.argv[1:]:
-    raw = subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
+        'l1tex__data_bank_conflicts_pipe_lsu_mem_shared.sum', 'l1tex__data_pipe_lsu_wavefronts_mem_shared.sum',
+        'smsp__sass_thread_inst_executed_op_ffma_pred_on.sum', 'smsp__sass_thread_inst_executed_op_fadd_pred_on.sum', 'sm__cycles_active.avg',
+        'smsp__inst_executed_op_local_ld.sum', 'smsp__inst_executed_op_local_st.sum', 'smsp__inst_executed_op_shared_ld.sum', 'smsp__inst_executed_op_shared_st.sum']
+def summary(rep):
+    raw = open(rep).read() if rep.endswith(".csv") else subprocess.run(["ncu", "-i", rep, "--page", "raw", "--csv"], capture_output=True, text=True).stdout
     rows = list(csv.reader(raw.splitlines()))
     h, u, v = rows[0], rows[1], rows[2]
-    print("==", rep)
+    out = {}
     for a, b, c in zip(h, u, v):
-        if a in WANT or ('issue_stalled' in a and 'per_issue_active' in a and float(c or 0) > 0.1):
+        try: big = float(c.replace(",", "") or 0) > 0.1
+        except ValueError: big = False
+        if a in WANT or ('issue_stalled' in a and 'per_issue_active' in a and big):
+            out[a] = (c, b)
+    return out
+if __name__ == "__main__":
+    for rep in sys.argv[1:]:
+        print("==", rep)
+        for a, (c, b) in summary(rep).items():
             print(f"{a:88s} {c:>16s} {b}")

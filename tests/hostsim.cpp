@@ -204,3 +204,28 @@ extern "C" int hostsim_clusters(const rt_sphere* spheres, unsigned n, float* out
     if (!(sc.cfilt[c].w == INFINITY)) return -2;
   return (int)sc.nc;
 }
+
+/* The work map of rt_core.cuh (groups of 32 items per tile; 8x4 tiles x samples, or 16x8 tiles x four pixel
+ * sub-lattices at 1 spp): every result record must be produced by exactly one item, and tile_of_dst must
+ * invert the map.  hits[localRows*W*spp] receives the number of items per record; returns the number of
+ * items whose tile_of_dst disagrees or whose frame row is not one of this shard's rows (must be 0). */
+extern "C" int hostsim_workmap(unsigned W, unsigned H, unsigned stripRows, unsigned stripFirst, unsigned stripStride,
+                               unsigned spp, unsigned nIter, unsigned* hits, unsigned* outLocalRows) {
+  const unsigned nStrips = (H + stripRows - 1) / stripRows;
+  unsigned localRows = 0;
+  for (unsigned s = stripFirst; s < nStrips; s += stripStride) localRows += (s * stripRows + stripRows <= H) ? stripRows : H - s * stripRows;
+  *outLocalRows = localRows;
+  const WorkMap m = make_workmap(W, localRows, stripRows, stripFirst, stripStride, spp, nIter);
+  int bad = 0;
+  for (uint32_t t = 0; t < m.nTiles; ++t)
+    for (uint32_t k = 0; k < m.K; ++k)
+      for (uint32_t wi = 0; wi < 32; ++wi) {
+        uint32_t gx, gy, dst; int si, sj;
+        if (!work_item(m, t, k, wi, gx, gy, dst, si, sj)) continue;
+        if (hits) hits[dst]++;
+        if (tile_of_dst(m, dst) != t) ++bad;
+        if (gx >= W || gy >= H || (gy / stripRows) % stripStride != stripFirst) ++bad;
+        if ((unsigned)(si * (int)nIter + sj) != (m.lattice ? 0u : k)) ++bad;
+      }
+  return bad;
+}

@@ -224,3 +224,25 @@ def test_cluster_filter_audit_under_rescaling(pkg, orc_mod, oracle, hostsim, see
         b, cb = hostsim(s, l, 48, 36, -4.0, 1.0, 8, mode=3)
         assert cb["accel_violations"] == 0, (seed, name)
         assert np.array_equal(orc_mod.canon(a), orc_mod.canon(b)), (seed, name)
+
+
+@pytest.mark.parametrize("W,H,alias,strip", [(64, 48, 1.0, (48, 0, 1)), (61, 37, 1.0, (37, 0, 1)), (61, 37, 2.0, (37, 0, 1)),
+                                             (200, 150, 3.0, (16, 1, 3)), (33, 70, 1.0, (4, 2, 8)), (130, 9, 1.0, (4, 0, 2)),
+                                             (7, 3, 1.0, (3, 0, 1)), (40, 40, 5.0, (4, 3, 4))])
+def test_work_map_covers_every_sample_once(W, H, alias, strip):
+    """rt_core.cuh WorkMap: groups of 32 items (8x4 tiles x samples, or 16x8 tiles x four pixel sub-lattices at
+    1 spp) produce every result record of the shard exactly once, on this shard's rows, and tile_of_dst inverts it."""
+    import ctypes
+    import __graft_entry__ as graft
+    lib = ctypes.CDLL(str(graft.build_hostsim()))
+    lib.hostsim_workmap.argtypes = [ctypes.c_uint] * 7 + [ctypes.c_void_p, ctypes.POINTER(ctypes.c_uint)]
+    lib.hostsim_workmap.restype = ctypes.c_int
+    n_iter = int(np.ceil(alias))
+    spp = n_iter * n_iter
+    rows, first, stride = strip
+    local = ctypes.c_uint(0)
+    hits = np.zeros(W * H * spp, np.uint32)            # at least localRows * W * spp
+    bad = lib.hostsim_workmap(W, H, rows, first, stride, spp, n_iter, hits.ctypes.data, ctypes.byref(local))
+    assert bad == 0
+    n = local.value * W * spp
+    assert n > 0 and (hits[:n] == 1).all() and (hits[n:] == 0).all()
