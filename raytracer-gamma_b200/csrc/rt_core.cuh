@@ -466,12 +466,8 @@ RT_HD uint32_t tile_of_dst(const WorkMap& m, uint32_t dst) {
   const uint32_t y = pix / m.W, x = pix - y * m.W;
   return m.lattice ? (y >> 3) * m.tilesX + (x >> 4) : (y >> 2) * m.tilesX + (x >> 3);
 }
-/* work order classes: a tile whose first group showed chains of >= RT_DEEP_AT queries goes out first */
-#define RT_ORDER_CLASSES 5
-#define RT_DEEP_AT 32
-RT_HD uint32_t order_class(uint32_t maxCount) {
-  return maxCount >= RT_DEEP_AT ? 0u : maxCount >= 16u ? 1u : maxCount >= 8u ? 2u : maxCount >= 2u ? 3u : 4u;
-}
+/* work order: a tile whose first group shows a chain of RT_DEEP_AT queries is handed out ahead of the others */
+#define RT_DEEP_AT 24
 
 /* The caller has already made `d` the current call's direction (s.rayD). */
 RT_HD void set_trace_query(Slot& s, Counters& ctr, V3 o, V3 d) {
@@ -526,7 +522,11 @@ RT_HD void setup_shadow_batch(Slot& s, const SceneView& sc) {
 
 /* The rays of a shadow batch (raytracer.h:279-286): from P towards each light, with the
  * squared distance to it.  Rebuilt by the pass that serves the batch. */
-struct ShadowGeo { V3 d[RT_SHADOW_BATCH]; float gap[RT_SHADOW_BATCH]; };
+struct ShadowGeo {
+  V3 d[RT_SHADOW_BATCH];        /* unit directions towards the lights of the batch                              */
+  float gap[RT_SHADOW_BATCH];   /* squared distances to them (also calculateMatte's divisor, raytracer.h:349)   */
+  float inc[RT_SHADOW_BATCH];   /* incidence N.d (raytracer.h:341-345), formed where the directions are         */
+};
 RT_HD void shadow_geo(const Slot& s, const SceneView& sc, ShadowGeo& g) {
 #ifdef __CUDACC__
 #pragma unroll
@@ -537,8 +537,9 @@ RT_HD void shadow_geo(const Slot& s, const SceneView& sc, ShadowGeo& g) {
       const V3 dir = vsub(mk(lp.x, lp.y, lp.z), s.P);
       g.gap[k] = vdot(dir, dir);
       g.d[k] = vunit_i(dir);       /* independent normalisations: inline so they overlap */
+      g.inc[k] = vdot(s.Nrm, g.d[k]);
     } else {
-      g.gap[k] = 0.f; g.d[k] = mk(0.f, 0.f, 0.f);
+      g.gap[k] = 0.f; g.d[k] = mk(0.f, 0.f, 0.f); g.inc[k] = 0.f;
     }
   }
 }
@@ -737,11 +738,12 @@ RT_HD bool advance(Slot& s, Frame* stack, Counters& ctr, const SceneView& sc, co
       if (k < s.ndirs) {
         ctr.rays++; ctr.shadow++;
         if (!((s.blocked >> k) & 1u)) {
-          const float4_ lp = sc.lpos[s.light + k], lc = sc.lcol[s.light + k];
-          const V3 dist = vsub(mk(lp.x, lp.y, lp.z), s.P);
-          const float incidence = vdot(s.Nrm, sg->d[k]);   /* d[k] = the vector calculateMatte rebuilds */
+          /* the pass that served the batch formed d = unit(light - P), |light - P|^2 and N.d: the vectors
+           * calculateMatte rebuilds (raytracer.h:336-349) are the same expressions on the same operands */
+          const float incidence = sg->inc[k];
           if (incidence > 0.f) {
-            const float kk = ex_div_i(incidence, vdot(dist, dist));
+            const float4_ lc = sc.lcol[s.light + k];
+            const float kk = ex_div_i(incidence, sg->gap[k]);
             s.lit = vadd(s.lit, vscale(kk, mk(lc.x, lc.y, lc.z)));
           }
         }

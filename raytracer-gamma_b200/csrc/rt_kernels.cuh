@@ -75,12 +75,6 @@ namespace rtg {
 #ifndef RT_SHADOW_INLINE_NORM
 #define RT_SHADOW_INLINE_NORM 0  /* the four normalisations of a shadow batch inline (they overlap) rather than out of line */
 #endif
-#ifndef RT_LOCKSTEP
-#define RT_LOCKSTEP 0            /* 1 | 2: groups of warps start every pass together (see trace_body) */
-#endif
-#ifndef RT_LOCK_WARPS
-#define RT_LOCK_WARPS 8          /* warps per lockstep group (8 = the CTA) */
-#endif
 #define RT_SLOTS 4               /* slots per lane (3 in shared memory when 4 do not fit beside the filter records) */
 
 struct TraceParams {
@@ -94,13 +88,12 @@ struct TraceParams {
   unsigned long long* counters;  /* [RT_NUM_COUNTERS], see rt_shim.cu                */
   WorkMap wm;               /* work items -> pixels and samples (rt_core.cuh)        */
   uint32_t total1, chunk;   /* items the queue head hands out (all of them, or the tiles' first groups), queue granule */
-  /* longest-chains-first work order (lpt = 1): see "Work order" below */
-  uint32_t lpt, kPerBlock, nBlocks, nEntries;
-  unsigned int* tileMax;    /* [nTiles] longest chain (queries) seen in the tile's first group      */
-  unsigned int* tileDone;   /* [nTiles] items of the first group that are finished (32 = all)        */
-  unsigned int* tilePushed; /* [nTiles] 1 once the tile's other groups are in a bucket               */
-  unsigned int* bucketEntries;   /* [RT_ORDER_CLASSES][nEntries] entry + 1 (0 = not written yet)     */
-  unsigned int* bucketCtl;  /* [0..4] tails, [8..12] heads, [16] entries handed out                  */
+  /* deep-tiles-first work order (lpt = 1): see "Work order" below */
+  uint32_t lpt, sweepStep, deepAt;
+  uint32_t lockstep;        /* 1: the warps of a CTA vote and start their passes together (see trace_body) */
+  unsigned int* tileClaimed;/* [nTiles] 1 once the tile's other groups have been handed out or listed */
+  unsigned int* deepList;   /* [nTiles] tile + 1 (0 = not written yet)                               */
+  unsigned int* orderCtl;   /* list tail, list head, sweep cursor                                    */
   int noFilter;             /* debug: exact test for every sphere                   */
   uint32_t list1Max;        /* accelerated mode: capacity of the per-lane (sub, cluster) lists */
 };
@@ -146,56 +139,58 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
 }
 
 /* ---- Work order -------------------------------------------------------------------------------------
- * A sample is a chain of dependent queries — a few for most samples, 30-130 for the ones that go through
+ * A sample is a chain of dependent queries — one or two for most samples, 30-130 for the ones that go through
  * refracting spheres — and a pass costs the same however few lanes it serves.  Handing the tiles out in
  * scanline order ends every launch on a few warps working off the deep samples they happened to start last
- * (8-10 ms per launch at 1 024 spheres: a tenth of a GPU's share of an 8K frame on eight GPUs).  So the queue
- * head hands out only every tile's FIRST group (sample 0, or the first pixel sub-lattice at 1 spp: a quarter
- * of the frame at most), the chain lengths of those samples classify the tile, and its remaining groups go
- * into one of RT_ORDER_CLASSES buckets that are drained deepest class first:
- *   - a first-group sample that reaches RT_DEEP_AT queries puts its tile into bucket 0 at once;
- *   - otherwise the tile is classified when all 32 items of its first group have finished.
- * Buckets are multi-producer / multi-consumer arrays in global memory (tail and head counters, entries
- * written after the tail has moved: a consumer waits for the entry it has claimed).  A warp that finds the
- * queue head exhausted and the buckets empty carries on with what it has in flight; the launch is over when
- * every entry has been handed out and worked off.  The frame does not depend on the order (samples are
- * independent, main.cpp:439). */
+ * (8-10 ms per launch at 1 024 spheres: a tenth of a GPU's share of an 8K frame on eight GPUs).  So:
+ *   1. the queue head hands out only every tile's FIRST group (sample 0, or the first pixel sub-lattice at
+ *      1 spp: a quarter of the frame at most);
+ *   2. a first-group sample that reaches RT_DEEP_AT queries marks its tile DEEP: the tile's other groups go
+ *      into the deep list at once (they see almost the same geometry);
+ *   3. once the queue head is exhausted a warp takes its work from the deep list while there is any, and
+ *      otherwise SWEEPS the tiles in scanline order, claiming those nobody has claimed yet.
+ * The deep tiles therefore start early and the launch ends on shallow ones.  The list is a multi-producer /
+ * multi-consumer array in global memory (entries are written after the tail has moved: a consumer waits for
+ * the entry it has claimed); a tile is claimed — by the deep trigger or by the sweep — with one atomicExch
+ * on tileClaimed[].  A warp is done when the sweep has passed the last tile, the list is empty and its own
+ * samples are finished; a tile marked deep after that is worked off by the warp that marked it.  The frame
+ * does not depend on the order (samples are independent, main.cpp:439). */
 __device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
+enum { ORD_TAIL = 0, ORD_HEAD = 1, ORD_SWEEP = 2 };     /* orderCtl words */
 
-__device__ __noinline__ void bucket_push(const TraceParams& p, uint32_t tile, uint32_t cls) {
-  for (uint32_t blk = 0; blk < p.nBlocks; ++blk) {
-    const unsigned pos = atomicAdd(&p.bucketCtl[cls], 1u);
-    atomicExch(&p.bucketEntries[(size_t)cls * p.nEntries + pos], tile * p.nBlocks + blk + 1u);
+/* A first-group sample of `tile` has just reached RT_DEEP_AT queries.  Out of line, called from converged code. */
+__device__ __noinline__ void mark_deep(const TraceParams& p, uint32_t tile) {
+  if (atomicExch(&p.tileClaimed[tile], 1u) == 0u) {
+    const unsigned pos = atomicAdd(&p.orderCtl[ORD_TAIL], 1u);
+    atomicExch(&p.deepList[pos], tile + 1u);
   }
 }
-/* one first-group item is finished (count = its chain length; 0 for an item outside the frame) */
-__device__ __noinline__ void first_group_done(const TraceParams& p, uint32_t tile, uint32_t count) {
-  if (count > 1u) atomicMax(&p.tileMax[tile], count);
-  if (atomicAdd(&p.tileDone[tile], 1u) + 1u == 32u && atomicExch(&p.tilePushed[tile], 1u) == 0u) {
-    const unsigned mx = ld_volatile(&p.tileMax[tile]);      /* a late atomicMax of another lane only costs order quality */
-    bucket_push(p, tile, order_class(mx > count ? mx : count));
-  }
-}
-__device__ __noinline__ void first_group_deep(const TraceParams& p, uint32_t tile) {
-  if (atomicExch(&p.tilePushed[tile], 1u) == 0u) bucket_push(p, tile, 0u);
-}
-/* next entry of the deepest non-empty bucket, or RT_NONE.  *allOut = every entry of the frame has been handed out. */
-__device__ __noinline__ uint32_t bucket_pop(const TraceParams& p, bool* allOut) {
-  for (uint32_t cls = 0; cls < RT_ORDER_CLASSES; ++cls) {
-    for (;;) {
-      const unsigned h = ld_volatile(&p.bucketCtl[8 + cls]), t = ld_volatile(&p.bucketCtl[cls]);
-      if (h >= t) break;
-      if (atomicCAS(&p.bucketCtl[8 + cls], h, h + 1u) == h) {
-        unsigned e;
-        while ((e = ld_volatile(&p.bucketEntries[(size_t)cls * p.nEntries + h])) == 0u) { }
-        atomicAdd(&p.bucketCtl[16], 1u);
-        *allOut = false;
-        return e - 1u;
-      }
+/* Next tiles for this warp (whole warp calls): up to RT_SWEEP_STEP tiles; bit l of the result = lane l holds a tile in
+ * *mine.  0 with *allOut = nothing is left to hand out; 0 without = the sweep step found only claimed tiles (call again). */
+__device__ __noinline__ unsigned next_tiles(const TraceParams& p, uint32_t lane, uint32_t* mine, bool* allOut) {
+  *allOut = false;
+  const unsigned c = (lane < 3u) ? ld_volatile(&p.orderCtl[lane]) : 0u;
+  const unsigned t = __shfl_sync(RT_FULL, c, ORD_TAIL), h = __shfl_sync(RT_FULL, c, ORD_HEAD), sw = __shfl_sync(RT_FULL, c, ORD_SWEEP);
+  if (h < t) {                                   /* the deep list first */
+    int ok = 0;
+    if (lane == 0) ok = atomicCAS(&p.orderCtl[ORD_HEAD], h, h + 1u) == h;
+    if (!__shfl_sync(RT_FULL, ok, 0)) return 0u;
+    if (lane == 0) {
+      unsigned e;
+      while ((e = ld_volatile(&p.deepList[h])) == 0u) { }
+      *mine = e - 1u;
     }
+    return 1u;
   }
-  *allOut = ld_volatile(&p.bucketCtl[16]) >= p.nEntries;
-  return RT_NONE;
+  if (sw >= p.wm.nTiles) { *allOut = true; return 0u; }
+  unsigned base = 0;
+  if (lane == 0) base = atomicAdd(&p.orderCtl[ORD_SWEEP], p.sweepStep);
+  base = __shfl_sync(RT_FULL, base, 0);
+  const unsigned tile = base + lane;
+  bool got = false;
+  if (lane < p.sweepStep && tile < p.wm.nTiles) got = atomicExch(&p.tileClaimed[tile], 1u) == 0u;
+  *mine = tile;
+  return __ballot_sync(RT_FULL, got);
 }
 
 /* ---- slot storage: the 21-word records of rt_core.cuh (slot_pack / slot_unpack), either interleaved in
@@ -459,7 +454,7 @@ __device__ __forceinline__ void pass_trace(const TraceParams& p, const ConstReco
  * same query with one direction, so it rides along for free and keeps the lane busy.
  * The rays of the batch (raytracer.h:279-286: the reference's own normalised vectors) stay in
  * registers, packed and negated, from the set-up through the loop to resolve and advance. */
-struct ShadowRays { Dir2 DP[RT_SHADOW_BATCH / 2]; float gap[RT_SHADOW_BATCH]; };
+struct ShadowRays { Dir2 DP[RT_SHADOW_BATCH / 2]; float gap[RT_SHADOW_BATCH], inc[RT_SHADOW_BATCH]; };
 __device__ __forceinline__ V3 shadow_dir(const ShadowRays& r, uint32_t sub) {
   const Dir2& q = (sub & 2u) ? r.DP[1] : r.DP[0];
   return (sub & 1u) ? mk(-hi_of(q.ndx), -hi_of(q.ndy), -hi_of(q.ndz)) : mk(-lo_of(q.ndx), -lo_of(q.ndy), -lo_of(q.ndz));
@@ -476,7 +471,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const ConstRec
   V3 org = mk(0.f, 0.f, 0.f);
   V3 riderD = mk(0.f, 0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; R.gap[k] = 0.f; }
+  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; R.gap[k] = 0.f; R.inc[k] = 0.f; }
   if (s0 >= 0) {
     org = st.ldv(s0, W_P);
     O = make_origin(org);
@@ -490,6 +485,7 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const ConstRec
     } else {
       const uint32_t hdr = st.at(s0, W_HDR);
       const int nd = (int)((hdr >> 2) & 7u), light = (int)((hdr >> 10) & 0x7FFFu);
+      const V3 nrm = st.ldv(s0, W_NRM);
 #pragma unroll
       for (int k = 0; k < ND; ++k) {
         if (k < nd) {
@@ -497,10 +493,12 @@ __device__ __forceinline__ void pass_shadow(const TraceParams& p, const ConstRec
           const V3 dir = vsub(mk(lp.x, lp.y, lp.z), org);     /* raytracer.h:279-286 */
           R.gap[k] = vdot(dir, dir);
 #if RT_SHADOW_INLINE_NORM
-          make_dir_unit(D[k], org, vunit_i(dir));       /* independent normalisations: inline so they overlap */
+          const V3 u = vunit_i(dir);                    /* independent normalisations: inline so they overlap */
 #else
-          make_dir_unit(D[k], org, vunit(dir));
+          const V3 u = vunit(dir);
 #endif
+          make_dir_unit(D[k], org, u);
+          R.inc[k] = vdot(nrm, u);                      /* raytracer.h:341-345, used when the batch is shaded */
           live |= 1u << k;
           if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
         }
@@ -775,7 +773,7 @@ __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx&
   V3 org = mk(0.f, 0.f, 0.f);
   V3 riderD = mk(0.f, 0.f, 0.f);
 #pragma unroll
-  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; R.gap[k] = 0.f; }
+  for (int k = 0; k < ND; ++k) { D[k].ndx = D[k].ndy = D[k].ndz = D[k].od = 0.f; R.gap[k] = 0.f; R.inc[k] = 0.f; }
   if (s0 >= 0) {
     org = st.ldv(s0, W_P);
     O = make_origin(org);
@@ -789,13 +787,16 @@ __device__ __forceinline__ void pass_shadow_accel(const TraceParams& p, WarpCtx&
     } else {
       const uint32_t hdr = st.at(s0, W_HDR);
       const int nd = (int)((hdr >> 2) & 7u), light = (int)((hdr >> 10) & 0x7FFFu);
+      const V3 nrm = st.ldv(s0, W_NRM);
 #pragma unroll
       for (int k = 0; k < ND; ++k) {
         if (k < nd) {
           const float4_ lp = p.sc.lpos[light + k];
           const V3 dir = vsub(mk(lp.x, lp.y, lp.z), org);
           R.gap[k] = vdot(dir, dir);
-          make_dir_unit(D[k], org, vunit(dir));
+          const V3 u = vunit(dir);
+          make_dir_unit(D[k], org, u);
+          R.inc[k] = vdot(nrm, u);
           live |= 1u << k;
           if (p.noFilter || !(ofil && dir_filterable(D[k]))) exact |= 1u << k;
         }
@@ -929,7 +930,8 @@ __device__ __forceinline__ void pass_contain_accel(const TraceParams& p, WarpCtx
  * (kind | ndirs << 4) tag for the lane's register-resident census. */
 template <class St>
 __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, const St& st, int sv, Frame* stack, Counters& ctr,
-                                                 float& laneMax, const ShadowGeo* sg, const Answer& ans) {
+                                                 float& laneMax, const ShadowGeo* sg, const Answer& ans, uint32_t& deepPixel) {
+  deepPixel = RT_NO_PIXEL;
   Slot s;
   bool done = false;
 #if RT_ADV_CONVERGENT
@@ -946,11 +948,8 @@ __device__ __forceinline__ uint32_t advance_slot(const TraceParams& p, const St&
   s.minT = ans.t; s.hitIdx = ans.h; s.blocked = ans.blocked;
   done = advance(s, stack, ctr, p.sc, p.cam, sg);
 #endif
-  if (s.first) {
-    /* the chain lengths of a tile's first group order its other groups (see "Work order") */
-    if (done) first_group_done(p, tile_of_dst(p.wm, s.pixel), (uint32_t)s.count);
-    else if (s.count == RT_DEEP_AT) first_group_deep(p, tile_of_dst(p.wm, s.pixel));
-  }
+  /* a first-group sample that turns out deep marks its tile (see "Work order"): done by the caller, out of line */
+  deepPixel = (s.first && !done && s.count == (int)p.deepAt) ? s.pixel : RT_NO_PIXEL;
   if (done) {
     const V3 v = sample_value(s, p.cam);
     if (p.spp == 1u) {
@@ -1033,28 +1032,29 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   uint32_t passT = 0, passS4 = 0, passC = 0;                /* passes by kind (warp-uniform) */
   uint32_t servedT = 0, servedS = 0, servedC = 0;            /* sub-queries of this lane served */
 
-  uint32_t wbase = 0, wend = 0;          /* warp-uniform slice of work: items wbase..wend-1 of the queue head or of a bucket entry */
-  uint32_t segTile = 0, segK0 = 0;       /* bucket entry: its tile and first group */
+  uint32_t wbase = 0, wend = 0;          /* warp-uniform slice of work: items wbase..wend-1 of the queue head or of a claimed tile */
+  uint32_t segTile = 0;                  /* a claimed tile: its groups 1..K-1 */
   bool segBucket = false, headDry = false;
+  uint32_t entMine = 0, entMask = 0;     /* tiles the warp has claimed and not started: bit l = lane l holds one */
   bool queueDry = false;                 /* nothing left to hand out: the warp finishes what it has in flight */
-#if RT_LOCKSTEP
-  __shared__ unsigned sVote[RT_BLOCK / 32 / RT_LOCK_WARPS][3][8];       /* a group's census of a round: nT, nS, nC, ndMax, warps not finished */
-  if (tid < (RT_BLOCK / 32 / RT_LOCK_WARPS) * 24) (&sVote[0][0][0])[tid] = 0u;
+  __shared__ unsigned sVote[3][8];       /* lockstep passes: the CTA's census of a round (nT, nS, nC, ndMax, warps not finished) */
+  if (tid < 24) (&sVote[0][0])[tid] = 0u;
   __syncthreads();
   int voteBuf = 0;
-#endif
 
   for (;;) {
-    /* ---- refill ---- */
-    bool starved = false;      /* the queue head is exhausted and the buckets are empty, but entries are still to come */
-#pragma unroll 1
-    for (int k = 0; k < NSLOTS && !queueDry && !starved; ++k) {
-      bool need = (((tags >> (8 * k)) & 0xFu) == (uint32_t)K_NULL);
-      while (!queueDry && !starved) {
+    /* ---- refill: every lane fills its first free slot, round after round until no lane has one ---- */
+    while (!queueDry) {
+      int k = -1;
+#pragma unroll
+      for (int j = NSLOTS - 1; j >= 0; --j)
+        if (((tags >> (8 * j)) & 0xFu) == (uint32_t)K_NULL) k = j;
+      bool need = k >= 0;
+      {
         const unsigned m = __ballot_sync(RT_FULL, need);
         if (m == 0) break;
         if (wbase >= wend) {
-          /* next slice of work (warp-uniform): the queue head first, then the buckets (see "Work order") */
+          /* next slice of work (warp-uniform): the queue head first, then deep and swept tiles (see "Work order") */
           if (!headDry) {
             uint32_t b = 0;
             if (lane == 0) b = atomicAdd(p.workCounter, p.chunk);
@@ -1063,24 +1063,22 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
             else { wbase = b; wend = (b + p.chunk < p.total1) ? b + p.chunk : p.total1; segBucket = false; }
           }
           if (headDry && wbase >= wend) {
-            uint32_t e = RT_NONE;
-            bool allOut = true;
-            if (p.lpt && lane == 0) e = bucket_pop(p, &allOut);
-            e = __shfl_sync(RT_FULL, e, 0);
-            allOut = __shfl_sync(RT_FULL, (int)allOut, 0) != 0;
-            if (e == RT_NONE) {
-              if (allOut) {
+            if (entMask == 0u) {
+              bool allOut = true;
+              if (p.lpt) entMask = next_tiles(p, lane, &entMine, &allOut);
+              if (entMask == 0u) {
+                if (!allOut) continue;              /* a sweep step over claimed tiles: take the next one */
                 queueDry = true;
 #ifdef RT_PHASE_TIMING
                 w.tDry = clock64();
 #endif
-              } else starved = true;
-              break;
+                break;
+              }
             }
-            segTile = e / p.nBlocks;
-            segK0 = 1u + (e - segTile * p.nBlocks) * p.kPerBlock;
-            const uint32_t kc = (p.wm.K - segK0 < p.kPerBlock) ? p.wm.K - segK0 : p.kPerBlock;
-            wbase = 0; wend = 32u * kc; segBucket = true;
+            const int src = __ffs((int)entMask) - 1;
+            entMask &= entMask - 1u;
+            segTile = __shfl_sync(RT_FULL, entMine, src);
+            wbase = 0; wend = 32u * (p.wm.K - 1u); segBucket = true;
           }
         }
         const uint32_t avail = wend - wbase;
@@ -1088,7 +1086,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
         if (need && rank < avail) {
           const uint32_t idx = wbase + rank, grp = idx >> 5;
           uint32_t tile, kk;
-          if (segBucket) { tile = segTile; kk = segK0 + grp; }
+          if (segBucket) { tile = segTile; kk = 1u + grp; }
           else if (p.lpt) { tile = grp; kk = 0u; }
           else { tile = grp / p.wm.K; kk = grp - tile * p.wm.K; }
           uint32_t gx, gy, dst;
@@ -1102,8 +1100,6 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
             store_slot(st, k, s);
             need = false;
             tags = (tags & ~(0xFFu << (8 * k))) | (((uint32_t)K_TRACE | (1u << 4)) << (8 * k));
-          } else if (p.lpt && kk == 0u) {
-            first_group_done(p, tile, 0u);        /* an item outside the frame still counts towards the tile's 32 */
           }
         }
         const uint32_t cnt = __popc(m);
@@ -1128,48 +1124,36 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
     unsigned nS = __reduce_add_sync(RT_FULL, (unsigned)ndS);
     unsigned nC = __reduce_add_sync(RT_FULL, (unsigned)((c0 >= 0) + (c1 >= 0)));
     int ndMax = __reduce_max_sync(RT_FULL, nd);
-#if RT_LOCKSTEP
-    /* Lockstep passes: the warps of a GROUP (RT_LOCK_WARPS warps of the CTA) start every pass together (one named
-     * barrier per pass), so that at any time a group executes one phase of a pass — the instruction working set of an
-     * SM is a few phases instead of sixteen (the kernel is ~75 KB of code against a 32 KB instruction cache; ncu: 44 %
-     * of the warp samples at 256 spheres are instruction-fetch stalls without it, 3 % with it).
-     * RT_LOCKSTEP 1: the group also votes together (equal loop lengths; a warp with nothing of the group's kind sits
-     * the pass out); 2: every warp keeps its own vote. */
-    {
-      const unsigned grp = (tid >> 5) / RT_LOCK_WARPS;
-      unsigned* vt = sVote[grp][voteBuf];
+    if (p.lockstep) {
+      /* Lockstep passes (small scenes): the warps of a CTA vote TOGETHER and start every pass together (one barrier
+       * per pass), so that at any time a CTA executes one phase of one pass kind — the instruction working set of
+       * an SM is two phases instead of sixteen.  The kernel is ~80 KB of code against a 32 KB instruction cache:
+       * at 256 spheres 44 % of the warp samples are instruction-fetch stalls without it and 3 % with it (ncu,
+       * profiles/r2).  Equal kinds also mean equal loop lengths, so the barrier costs little; a warp with nothing
+       * of the CTA's kind sits the pass out.  Large scenes run free: their passes are long loops out of a 3 KB
+       * body, and the common vote would cost them fill. */
+      unsigned* vt = sVote[voteBuf];
       const bool idle = (nT | nS | nC) == 0u;
       if (lane == 0) {
-#if RT_LOCKSTEP == 1
         if (nT) atomicAdd(&vt[0], nT);
         if (nS) atomicAdd(&vt[1], nS);
         if (nC) atomicAdd(&vt[2], nC);
         if (ndMax) atomicMax(&vt[3], (unsigned)ndMax);
-#endif
         if (!(idle && queueDry)) atomicAdd(&vt[4], 1u);
       }
-      asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "r"(32u * RT_LOCK_WARPS) : "memory");
+      __syncthreads();
       const unsigned cT = vt[0], cS = vt[1], cC = vt[2], cNd = vt[3], cLive = vt[4];
       /* three buffers in rotation: clear the PREVIOUS round's (every read of it came before the barrier above, its
        * next use comes after the next barrier) */
-      if ((tid & (32u * RT_LOCK_WARPS - 1u)) < 5u) sVote[grp][(voteBuf + 2) % 3][tid & 7u] = 0u;
+      if (tid < 5u) sVote[(voteBuf + 2) % 3][tid] = 0u;
       voteBuf = (voteBuf + 1) % 3;
       if (cLive == 0u) break;
-      if (idle && starved) __nanosleep(200);
-#if RT_LOCKSTEP == 1
       if ((cT | cS | cC) == 0u) continue;
       nT = cT; nS = cS; nC = cC; ndMax = (int)cNd;
-#else
-      if (idle) continue;
-#endif
-    }
-#else
-    if ((nT | nS | nC) == 0u) {
+    } else if ((nT | nS | nC) == 0u) {
       if (queueDry) break;
-      if (starved) __nanosleep(200);
       continue;
     }
-#endif
     /* serve the kind that fills the largest share of its pass: capacity 64 sub-queries for
      * trace / contain passes, 32 x (2 or 4) for a shadow pass (scenes with <= 2 lights fill half of it) */
     const unsigned capS = (ndMax <= 2) ? 64u : 128u;
@@ -1178,9 +1162,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
                      : (nT >= nC) ? K_TRACE : K_CONTAIN;
     const int sv0 = (mode == K_SHADOW) ? sOrT : (mode == K_TRACE) ? t0 : c0;
     const int sv1 = (mode == K_SHADOW) ? -1 : (mode == K_TRACE) ? t1 : c1;
-#if RT_LOCKSTEP == 1
-    if (!__any_sync(RT_FULL, sv0 >= 0)) continue;      /* nothing of the group's kind in this warp */
-#endif
+    if (p.lockstep && !__any_sync(RT_FULL, sv0 >= 0)) continue;      /* nothing of the CTA's kind in this warp */
     Answer a0, a1;
     a0.t = a1.t = 1000.f; a0.h = a1.h = -1; a0.blocked = a1.blocked = 0u;
     ShadowGeo sg;
@@ -1193,7 +1175,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
       if (s0 >= 0) servedS += (unsigned)nd; else servedT += (unsigned)ndS;
       /* the rays of the batch just served, as the state machine reads them */
 #pragma unroll
-      for (int k = 0; k < RT_SHADOW_BATCH; ++k) { sg.d[k] = shadow_dir(R, (uint32_t)k); sg.gap[k] = R.gap[k]; }
+      for (int k = 0; k < RT_SHADOW_BATCH; ++k) { sg.gap[k] = R.gap[k]; sg.inc[k] = R.inc[k]; }
     } else if (mode == K_TRACE) {
       if (ACCEL) pass_trace_accel(p, w, st, t0, t1, ctr, a0, a1);
       else pass_trace<USE_CONST>(p, cr, w, st, t0, t1, ctr, a0, a1);
@@ -1208,8 +1190,12 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
     for (int r = 0; r < 2; ++r) {
       const int sv = r ? sv1 : sv0;
       if (!__any_sync(RT_FULL, sv >= 0)) continue;
-      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * RT_MAX_STACK], ctr, laneMax, &sg, r ? a1 : a0);
+      uint32_t deepPixel;
+      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * RT_MAX_STACK], ctr, laneMax, &sg, r ? a1 : a0, deepPixel);
       if (sv >= 0) tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
+      if (__any_sync(RT_FULL, deepPixel != RT_NO_PIXEL)) {
+        if (deepPixel != RT_NO_PIXEL) mark_deep(p, tile_of_dst(p.wm, deepPixel));
+      }
     }
     RT_TICK(4);
   }

@@ -19,7 +19,7 @@ using namespace rtg;
 #ifndef RT_DEFAULT_SLOTS
 #define RT_DEFAULT_SLOTS 4
 #endif
-#define RT_K_PER_ENTRY 8u            /* groups of one tile per bucket entry (work order) */
+#define RT_LOCKSTEP_MAX_SPHERES 512u  /* lockstep passes up to this many filter records (rt_kernels.cuh trace_body) */
 #define RT_COPY_CHUNK (8u << 20)     /* pageable readback: D2H and the host memcpy alternate over two pinned chunks */
 #define RT_FLUSH_BYTES (256u << 20)  /* rt_cuda_flush_l2: larger than the 126 MB L2 */
 
@@ -74,7 +74,9 @@ struct rt_cuda_ctx {
 
   /* options */
   int staging = 0, noFilter = 0, blocksPerSM = 0, slots = 0;
-  int order = 1;                   /* 1: longest chains first (default) | 0: tiles in scanline order */
+  int order = 0;                   /* 0 auto (= 1) | 1: deep tiles first | 2: tiles in scanline order */
+  int sweepStep = 0, deepAt = 0;   /* work-order tuning (0 = default) */
+  int lockstep = 0;                /* 0 auto (scenes of <= RT_LOCKSTEP_MAX_SPHERES records) | 1 on | 2 off */
   int slotMode = 0;                /* 0 auto | 1 slot records in shared memory | 2 in local memory */
   int accel = 0;                   /* 1: two-level cluster filter (optional accelerated mode) */
   uint32_t nc = 0, ncPad = 0;
@@ -220,7 +222,10 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!strcmp(key, "no_filter")) { ctx->noFilter = value ? 1 : 0; return RT_CUDA_OK; }
   if (!strcmp(key, "accel")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->accel = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "order")) { ctx->order = value ? 1 : 0; return RT_CUDA_OK; }
+  if (!strcmp(key, "order")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->order = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "lockstep")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->lockstep = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "sweep_step")) { if (value < 0 || value > 32) return RT_CUDA_ERR_INVALID_ARG; ctx->sweepStep = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "deep_at")) { if (value < 0 || value > RT_COUNT_MAX) return RT_CUDA_ERR_INVALID_ARG; ctx->deepAt = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "slot_mode")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->slotMode = (int)value; return RT_CUDA_OK; }
 #ifdef RT_DEV_VARIANTS   /* development builds only: slot-count variants of the local-memory kernel */
   if (!strcmp(key, "slots")) { if (value != 0 && (value < 3 || value > 4)) return RT_CUDA_ERR_INVALID_ARG; ctx->slots = (int)value; return RT_CUDA_OK; }
@@ -313,12 +318,9 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   const uint32_t spp = (uint32_t)spp64;
   p.wm = make_workmap(width, localRows, stripRows, stripFirst, stripStride, spp, (uint32_t)p.cam.nIter);
   if ((uint64_t)p.wm.tilesX * p.wm.tilesY * 32u * p.wm.K >= (1ull << 32)) return RT_CUDA_ERR_TOO_LARGE;
-  /* work order: every tile's first group from the queue head, the other groups deepest tiles first (rt_kernels.cuh
-   * "Work order"); bucket entries cover RT_K_PER_ENTRY groups of one tile */
-  const bool lpt = ctx->order != 0 && p.wm.K > 1u;
-  const uint32_t nBlocks = (p.wm.K - 1u + RT_K_PER_ENTRY - 1u) / RT_K_PER_ENTRY;
-  const uint64_t nEntries64 = (uint64_t)p.wm.nTiles * nBlocks;
-  if (nEntries64 >= (1ull << 31)) return RT_CUDA_ERR_TOO_LARGE;
+  /* work order: every tile's first group from the queue head, then the tiles marked deep, then a sweep over the
+   * rest (rt_kernels.cuh "Work order") */
+  bool lpt = ctx->order != 2 && p.wm.K > 1u;
 
   /* the accelerated mode needs something to cull, its records in shared memory, and the cluster form */
   const size_t listBytes = (size_t)RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short);
@@ -380,11 +382,14 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
     if (grid > needBlocks) grid = needBlocks;
     if (grid < 1) grid = 1;
   }
+  /* ... which needs the first groups to last long enough for deep samples to show: several times the samples in flight
+   * (measured: a 68-row shard of the 8K frame is 7 % slower with it, a 540-row shard 4.6 % faster) */
+  if (ctx->order == 0 && (uint64_t)p.wm.nTiles * 32u < 4ull * grid * RT_BLOCK * RT_SLOTS) lpt = false;
   int rc = ensure_dev(ctx, ctx->dFb, ctx->fbCap, pixels ? pixels : 1);
   if (rc) { ctx->haveFrame = false; return rc; }
-  const size_t words = 32 + 3 * (size_t)p.wm.nTiles + (size_t)RT_ORDER_CLASSES * (size_t)nEntries64;
+  const size_t orderWords = 32 + 2 * (size_t)p.wm.nTiles;
   if (lpt && pixels) {
-    rc = ensure_dev(ctx, ctx->dOrder, ctx->orderCap, words);
+    rc = ensure_dev(ctx, ctx->dOrder, ctx->orderCap, orderWords);
     if (rc) { ctx->haveFrame = false; return rc; }
   }
   if (spp > 1 && pixels) {
@@ -415,16 +420,19 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   p.counters = ctx->dCounters;
   p.lpt = lpt ? 1u : 0u;
   p.total1 = lpt ? p.wm.nTiles * 32u : totalWork;
-  p.kPerBlock = RT_K_PER_ENTRY; p.nBlocks = nBlocks; p.nEntries = (uint32_t)nEntries64;
-  p.tileMax = p.tileDone = p.tilePushed = p.bucketEntries = p.bucketCtl = nullptr;
+  p.sweepStep = 1u;     /* one tile per claim: 4 and 8 measured slower (neighbouring deep tiles land on one warp) */
+  if (ctx->sweepStep) p.sweepStep = (uint32_t)ctx->sweepStep;
+  /* lockstep passes where the per-pass loop is short: few records (the accelerated mode loops over clusters) */
+  const uint32_t loopRecords = accel ? ctx->ncPad : ctx->nPad;
+  p.lockstep = (ctx->lockstep == 1 || (ctx->lockstep == 0 && loopRecords <= RT_LOCKSTEP_MAX_SPHERES)) ? 1u : 0u;
+  p.deepAt = ctx->deepAt ? (uint32_t)ctx->deepAt : RT_DEEP_AT;
+  p.tileClaimed = p.deepList = p.orderCtl = nullptr;
   if (lpt) {
-    /* one zeroed allocation: bucket control (32 words) | tileMax | tileDone | tilePushed | entries[classes][nEntries] */
-    CU(cudaMemsetAsync(ctx->dOrder, 0, words * sizeof(unsigned int), ctx->stream));
-    p.bucketCtl = ctx->dOrder;
-    p.tileMax = ctx->dOrder + 32;
-    p.tileDone = p.tileMax + p.wm.nTiles;
-    p.tilePushed = p.tileDone + p.wm.nTiles;
-    p.bucketEntries = p.tilePushed + p.wm.nTiles;
+    /* one zeroed allocation: control words (32) | tileClaimed[nTiles] | deepList[nTiles] */
+    CU(cudaMemsetAsync(ctx->dOrder, 0, orderWords * sizeof(unsigned int), ctx->stream));
+    p.orderCtl = ctx->dOrder;
+    p.tileClaimed = ctx->dOrder + 32;
+    p.deepList = p.tileClaimed + p.wm.nTiles;
   }
   p.spp = spp;
   p.samples = (spp > 1) ? ctx->dSamples : nullptr;

@@ -192,7 +192,9 @@ int main(int argc, char** argv) {
   uint64_t qhead = 0;
   /* order=9: dynamic buckets.  Phase 1 = sample 0 of every tile from the queue; a tile's other samples are pushed into a
    * bucket when one of its phase-1 samples reaches `deepAt` queries (bucket 0) or when all 32 have completed (by class) */
-  const bool dyn = P.order == 9;
+  const bool dyn = P.order == 9 || P.order == 10;
+  const bool sweep = P.order == 10;     /* only the deep trigger pushes; everything else is swept in tile order */
+  uint64_t sweepNext = 0;
   const uint64_t nTilesD = nGroups / gF.spp;
   std::vector<uint8_t> tPushed(dyn ? nTilesD : 0, 0), tDone(dyn ? nTilesD : 0, 0), tMax(dyn ? nTilesD : 0, 0);
   std::vector<std::vector<uint32_t>> bucket(8); std::vector<size_t> bhead(8, 0);
@@ -226,8 +228,15 @@ int main(int argc, char** argv) {
             if (qhead < nTilesD * 32) { w.wbase = (uint32_t)qhead; w.wend = (uint32_t)std::min<uint64_t>(qhead + chunk, nTilesD * 32); qhead += chunk; w.phase2 = false; }
             else {
               int b = 0; while (b < 8 && bhead[b] >= bucket[b].size()) ++b;
+              uint32_t t;
+              if (b == 8 && sweep) {
+                while (sweepNext < nTilesD && tPushed[sweepNext]) ++sweepNext;
+                if (sweepNext >= nTilesD) { w.dry = true; w.dryAt = now; w.starved = true; break; }
+                t = (uint32_t)sweepNext; tPushed[t] = 1; ++tilesConsumed;
+              } else {
               if (b == 8) { if (tilesConsumed == nTilesD) { w.dry = true; w.dryAt = now; } w.starved = true; break; }
-              const uint32_t t = bucket[b][bhead[b]++]; ++tilesConsumed;
+              t = bucket[b][bhead[b]++]; ++tilesConsumed;
+              }
               w.wbase = 0; w.wend = 32 * (gF.spp - 1); w.phase2 = true; w.tile = t;
             }
           } else
@@ -294,7 +303,7 @@ int main(int argc, char** argv) {
         const uint64_t t = (s.item >> 5) / gF.spp;
         tMax[t] = (uint8_t)std::max<unsigned>(tMax[t], std::min<unsigned>(s.pos, 255));
         if (fin) tDone[t]++;
-        if (!tPushed[t] && ((int)s.pos >= P.deepAt || tDone[t] == 32)) { tPushed[t] = 1; bucket[class_of(tMax[t])].push_back((uint32_t)t); }
+        if (!tPushed[t] && ((int)s.pos >= P.deepAt || (!sweep && tDone[t] == 32))) { tPushed[t] = 1; bucket[sweep ? 0 : class_of(tMax[t])].push_back((uint32_t)t); }
       }
       if (fin) s.item = -1;
     };

@@ -129,6 +129,21 @@ def test_staging_and_filter_variants_agree(pkg, orc_mod, gpu):
     assert st1["staging"] == 1 and st2["staging"] == 2
 
 
+def test_work_order_and_lockstep_variants_agree(pkg, orc_mod, oracle, gpu):
+    """The work order (deep tiles first / scanline), its tuning knobs, lockstep passes and the slot placement are
+    scheduling only: same frame, same ray count, for 1 spp (pixel sub-lattices) and for several samples per pixel,
+    on a frame large enough for every queue phase (first groups, deep list, sweep) to be exercised."""
+    sph, lgt = pkg.synth_scene(300, 4, seed=5)
+    for W, H, alias in ((601, 403, 1.0), (320, 200, 2.0), (97, 61, 3.0)):
+        ref, ctr = oracle.render(sph, lgt, W, H, -4.0, alias, 8)
+        for opts in ({}, {"order": 1}, {"order": 2}, {"order": 1, "lockstep": 1}, {"order": 1, "lockstep": 2}, {"order": 2, "lockstep": 1},
+                     {"order": 1, "sweep_step": 3, "deep_at": 6}, {"order": 1, "deep_at": 2, "sweep_step": 8, "lockstep": 2},
+                     {"order": 1, "slot_mode": 2, "deep_at": 4}, {"order": 1, "accel": 2, "deep_at": 3}):
+            fb, _, st = _render(gpu, sph, lgt, W, H, -4.0, alias, 8, **opts)
+            assert np.array_equal(orc_mod.canon(fb), orc_mod.canon(ref)), (W, H, alias, opts)
+            assert st["rays"] == ctr["rays"] and st["samples"] == ctr["samples"], (W, H, alias, opts)
+
+
 def test_edge_cases(pkg, orc_mod, oracle, gpu):
     sph, lgt = pkg.default_scene()
     # empty scene, no lights, 1-pixel-high and non-tile-multiple frames, sub-unit alias
