@@ -183,12 +183,16 @@ __device__ __noinline__ unsigned next_tiles(const TraceParams& p, uint32_t lane,
     return 1u;
   }
   if (sw >= p.wm.nTiles) { *allOut = true; return 0u; }
+  /* guided step: several tiles per claim while plenty are left (a claim is two or three dependent round trips to
+   * L2 for ~100 items each), single tiles towards the end of the sweep where balance matters */
+  unsigned step = (p.wm.nTiles - sw) / (gridDim.x * (RT_BLOCK / 32u) * 2u);
+  step = step < 1u ? 1u : step > p.sweepStep ? p.sweepStep : step;
   unsigned base = 0;
-  if (lane == 0) base = atomicAdd(&p.orderCtl[ORD_SWEEP], p.sweepStep);
+  if (lane == 0) base = atomicAdd(&p.orderCtl[ORD_SWEEP], step);
   base = __shfl_sync(RT_FULL, base, 0);
   const unsigned tile = base + lane;
   bool got = false;
-  if (lane < p.sweepStep && tile < p.wm.nTiles) got = atomicExch(&p.tileClaimed[tile], 1u) == 0u;
+  if (lane < step && tile < p.wm.nTiles) got = atomicExch(&p.tileClaimed[tile], 1u) == 0u;
   *mine = tile;
   return __ballot_sync(RT_FULL, got);
 }
