@@ -61,6 +61,24 @@ RT_HD double exd_sub(double a, double b) { return __dadd_rn(a, -b); }
 RT_HD double exd_mul(double a, double b) { return __dmul_rn(a, b); }
 RT_HD_NI double exd_div(double a, double b) { return __ddiv_rn(a, b); }
 RT_HD_NI double exd_sqrt(double a) { return __dsqrt_rn(a); }
+/* sin = (float)sqrt(1.0 - (double)(c*c)) as raytracer.h:683 computes it, for -1 < c < 1 (or NaN).
+ * The library's IEEE double square root is ~290 instructions (special cases, denormals); its argument here is
+ * always a normal number in (2^-24, 1], so the plain Markstein sequence — reciprocal-square-root seed (MUFU.RSQ64H),
+ * two coupled Newton steps, one exact-residual correction — gives the same correctly rounded double in 14
+ * (tests/fuzz_filter.cu checks it against __dsqrt_rn for EVERY float c in [0, 1)). */
+RT_HD float sin_from_cos(float c) {
+  const double x = __dadd_rn(1.0, -(double)__fmul_rn(c, c));
+  double y;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(y) : "d"(x));
+  double g = __dmul_rn(x, y), h = __dmul_rn(0.5, y);
+  double r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+  r = __fma_rn(-g, h, 0.5);
+  g = __fma_rn(g, r, g); h = __fma_rn(h, r, h);
+  const double d = __fma_rn(-g, g, x);
+  g = __fma_rn(d, h, g);
+  return (float)g;
+}
 RT_HD float fast_fma(float a, float b, float c) { return __fmaf_rn(a, b, c); }
 #else
 /* host build: compiled with -ffp-contract=off, so these stay separate operations */
@@ -76,6 +94,7 @@ RT_HD double exd_sub(double a, double b) { return a - b; }
 RT_HD double exd_mul(double a, double b) { return a * b; }
 RT_HD double exd_div(double a, double b) { return a / b; }
 RT_HD double exd_sqrt(double a) { return sqrt(a); }
+RT_HD float sin_from_cos(float c) { return (float)sqrt(1.0 - (double)(c * c)); }
 RT_HD float fast_fma(float a, float b, float c) { return fmaf(a, b, c); }
 #endif
 
@@ -547,36 +566,45 @@ RT_HD void shadow_geo(const Slot& s, const SceneView& sc, ShadowGeo& g) {
 /* Pop suspended calls until one launches a child ray or the stack is empty
  * (raytracer.h:552-628).  Returns true when the sample is finished. */
 RT_HD bool unwind(Slot& s, Frame* stack, Counters& ctr, const Camera& cam) {
-  while (s.top >= 0) {
-    Frame& f = stack[s.top];
+  if (s.top < 0) return true;
+  /* The frames live in local memory (an L2 round trip each) and the frames of consecutive levels are independent
+   * loads: the next level's words are requested while the current level is being combined, so popping k levels
+   * costs one memory latency instead of k (ncu, 256 spheres: 6.5 % of all warp samples waited here). */
+  V3 col = stack[s.top].colour, rc = stack[s.top].reflCol;
+  int tag = stack[s.top].tag;
+  for (;;) {
+    const int lvl = s.top;
+    V3 ncol = mk(0.f, 0.f, 0.f), nrc = ncol;
+    int ntag = 0;
+    if (lvl > 0) { ncol = stack[lvl - 1].colour; nrc = stack[lvl - 1].reflCol; ntag = stack[lvl - 1].tag; }
     --s.top;
-    s.colour = vadd(s.result, f.colour);
-    if (frame_stage(f) == 1) {
-      if (significant(f.reflCol)) {
-        /* re-push as stage 2 (always fits: the slot was just vacated) */
-        ++s.top;
-        f.colour = s.colour; f.tag = frame_tag(2, frame_medium(f));
-        s.result = s.colour;
-        if (s.top < cam.S - 1) {
-          /* reflected child, raytracer.h:602-611 */
-          s.rayD = f.reflD; s.rayI = f.reflCol; s.medium = frame_medium(f);
-          s.colour = mk(0.f, 0.f, 0.f);
-          set_trace_query(s, ctr, f.reflO, f.reflD);
-          return false;
-        }
-        /* child push dropped (raytraceStack.h:52): fall through to pop stage 2 */
-        continue;
+    s.colour = vadd(s.result, col);
+    if ((tag >> 16) == 1 && significant(rc)) {
+      /* re-push as stage 2 (always fits: the slot was just vacated) */
+      ++s.top;
+      Frame& f = stack[lvl];
+      const int medium = tag & 0xFFFF;
+      f.colour = s.colour; f.tag = frame_tag(2, medium);
+      s.result = s.colour;
+      if (s.top < cam.S - 1) {
+        /* reflected child, raytracer.h:602-611 */
+        s.rayD = f.reflD; s.rayI = rc; s.medium = medium;
+        s.colour = mk(0.f, 0.f, 0.f);
+        set_trace_query(s, ctr, f.reflO, f.reflD);
+        return false;
       }
-      s.result = s.colour;
-    } else {
-      s.result = s.colour;
+      /* child push dropped (raytraceStack.h:52): the frame just written is popped again as stage 2 */
+      col = s.colour; tag = frame_tag(2, medium);
+      continue;
     }
+    s.result = s.colour;
+    if (lvl == 0) return true;
+    col = ncol; rc = nrc; tag = ntag;
   }
-  return true;
 }
 
 /* raytracer.h:370-403 */
-RT_HD float fresnel_term(float n1, float n2, float cosA1, float cosA2) {
+RT_HD_NI float fresnel_term(float n1, float n2, float cosA1, float cosA2) {
   const float left = ex_mul(n1, cosA1);
   const float right = ex_mul(n2, cosA2);
   const double num = (double)ex_sub(left, right);
@@ -607,7 +635,7 @@ RT_HD int after_contain(Slot& s, Frame* stack, Counters& ctr, const SceneView& s
   float sinA1 = 0.f;
   if (cosA1 <= -1.0f) { cosA1 = -1.f; }
   else if (cosA1 >= 1.f) { cosA1 = 1.f; }
-  else { sinA1 = (float)exd_sqrt(exd_sub(1.0, (double)ex_mul(cosA1, cosA1))); }   /* :683, double */
+  else { sinA1 = sin_from_cos(cosA1); }                  /* :683, double */
 
   const float n1 = medB.w, n2 = tgtB.w;
   const float ratio = ex_div(n1, n2);

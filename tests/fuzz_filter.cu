@@ -142,3 +142,32 @@ extern "C" int fuzz_filter(uint64_t seed, uint32_t nSpheres, uint32_t rays, floa
   if (e != cudaSuccess) { fprintf(stderr, "fuzz_filter: %s\n", cudaGetErrorString(e)); return -2; }
   return 0;
 }
+
+/* sin_from_cos (rt_core.cuh) against the IEEE double square root it replaces, for EVERY float c in [0, 1)
+ * (c and -c square to the same value).  out[0] = values checked, out[1] = MISMATCHES (must be 0). */
+__global__ void sqrt_check_kernel(unsigned long long* out) {
+  unsigned long long n = 0, bad = 0;
+  const uint32_t stride = gridDim.x * blockDim.x;
+  for (uint32_t bits = blockIdx.x * blockDim.x + threadIdx.x; bits < 0x3F800000u; bits += stride) {
+    const float c = __uint_as_float(bits);
+    const float want = (float)__dsqrt_rn(__dadd_rn(1.0, -(double)__fmul_rn(c, c)));
+    const float got = sin_from_cos(c);
+    ++n;
+    if (__float_as_uint(want) != __float_as_uint(got)) ++bad;
+  }
+  for (int o = 16; o > 0; o >>= 1) { n += __shfl_xor_sync(0xFFFFFFFFu, n, o); bad += __shfl_xor_sync(0xFFFFFFFFu, bad, o); }
+  if ((threadIdx.x & 31) == 0) { atomicAdd(&out[0], n); if (bad) atomicAdd(&out[1], bad); }
+}
+extern "C" int fuzz_sin_from_cos(uint64_t out[2]) {
+  unsigned long long* dO = nullptr;
+  if (cudaMalloc(&dO, 2 * sizeof(unsigned long long)) != cudaSuccess) return -1;
+  cudaMemset(dO, 0, 2 * sizeof(unsigned long long));
+  sqrt_check_kernel<<<148 * 16, 256>>>(dO);
+  const cudaError_t e = cudaDeviceSynchronize();
+  unsigned long long h[2] = {0, 0};
+  cudaMemcpy(h, dO, sizeof h, cudaMemcpyDeviceToHost);
+  out[0] = h[0]; out[1] = h[1];
+  cudaFree(dO);
+  if (e != cudaSuccess) { fprintf(stderr, "fuzz_sin_from_cos: %s\n", cudaGetErrorString(e)); return -2; }
+  return 0;
+}
