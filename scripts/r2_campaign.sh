@@ -35,7 +35,13 @@ if [ $N -eq 1 ]; then
   for wl in config1 config2; do run_bench 1 $wl; done
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err; echo "reference arm rc=$?"
 fi
-timeout 900 python scripts/sweep.py --gpus $N > $O/sweep_config5_n$N.jsonl 2> $O/sweep_n$N.err; echo "sweep rc=$?"; tail -3 $O/sweep_config5_n$N.jsonl | cut -c1-260
+if [ $N -eq 1 ]; then
+  # the ncu launch list of the bench command (cold-cache, serialised: shares, not absolute times)
+  timeout 900 ncu --metrics gpu__time_duration.sum --clock-control none -c 400 --csv --log-file $O/ncu_launches_bench.csv \
+    python bench.py --steps 2 --warmup 1 --no-cpu-baseline --no-accel > $O/ncu_launches_bench.log 2>&1; echo "ncu launch list rc=$?"
+  { echo "== OpenCL ICD probe"; ls -la /etc/OpenCL/vendors 2>&1; ls /usr/lib/x86_64-linux-gnu 2>/dev/null | grep -i -E "opencl"; ldconfig -p | grep -i opencl; which clinfo; echo "(end)"; } > $O/opencl_probe.txt 2>&1
+fi
+[ "${3:-}" = "nosweep" ] || timeout 900 python scripts/sweep.py --gpus $N > $O/sweep_config5_n$N.jsonl 2> $O/sweep_n$N.err; echo "sweep rc=$?"; tail -3 $O/sweep_config5_n$N.jsonl | cut -c1-260
 if [ $N -gt 1 ]; then
   timeout 600 raytracer-gamma_b200/rt_gamma --gpus $N --spheres 1024 --width 7680 --height 4320 --alias 2 --depth 8 --frames 3 --out $O/frame.ppm > $O/rt_gamma_multi.txt 2>&1; echo "rt_gamma rc=$?"
   md5sum $O/frame.ppm >> $O/rt_gamma_multi.txt; tail -8 $O/rt_gamma_multi.txt; rm -f $O/frame.ppm
