@@ -311,16 +311,53 @@ RT_HD bool contains_exact(float4_ g, V3 p) {
 /* ---- suspended calls -------------------------------------------------------- */
 #define RT_MAX_STACK 16
 #define RT_SHADOW_BATCH 4
-struct Frame {            /* 13 words */
+/* A suspended call: 13 words laid out as one 64-byte chunk = two 32-byte sectors.  Every pop reads the first
+ * sector (colour, tag, reflection intensity: see unwind); only a pop that launches the reflected child reads the
+ * second (the pre-computed ray). */
+struct
+#if defined(__CUDACC__)
+__align__(16)
+#endif
+Frame {
   V3 colour;              /* cur.colour at suspension                                  */
-  V3 reflCol;             /* reflection intensity (raytracer.h:563-578)                */
-  V3 reflO;               /* pre-computed reflected ray (raytracer.h:817-842)           */
-  V3 reflD;
   int tag;                /* stage << 16 | medium: stage 1 waits for the refracted child, 2 for the reflected one */
+  V3 reflCol;             /* reflection intensity (raytracer.h:563-578)                */
+  int pad0;
+  V3 reflO;               /* pre-computed reflected ray (raytracer.h:817-842)           */
+  int pad1;
+  V3 reflD;
+  int pad2;
 };
 RT_HD int frame_tag(int stage, int medium) { return (stage << 16) | medium; }
 RT_HD int frame_stage(const Frame& f) { return f.tag >> 16; }
 RT_HD int frame_medium(const Frame& f) { return f.tag & 0xFFFF; }
+/* Frame traffic: 16-byte vector accesses that bypass L1 (a frame is written once and read once, many passes later;
+ * the small L1 left beside the slot records is better spent on the scene's geometry and material records). */
+#if defined(__CUDA_ARCH__)
+RT_HD void frame_load_hot(const Frame* f, V3& colour, V3& reflCol, int& tag) {
+  const float4 a = __ldcg(reinterpret_cast<const float4*>(f)), b = __ldcg(reinterpret_cast<const float4*>(f) + 1);
+  colour = mk(a.x, a.y, a.z); tag = __float_as_int(a.w); reflCol = mk(b.x, b.y, b.z);
+}
+RT_HD void frame_load_ray(const Frame* f, V3& reflO, V3& reflD) {
+  const float4 c = __ldcg(reinterpret_cast<const float4*>(f) + 2), d = __ldcg(reinterpret_cast<const float4*>(f) + 3);
+  reflO = mk(c.x, c.y, c.z); reflD = mk(d.x, d.y, d.z);
+}
+RT_HD void frame_store_head(Frame* f, V3 colour, int tag) {
+  __stcg(reinterpret_cast<float4*>(f), make_float4(colour.x, colour.y, colour.z, __int_as_float(tag)));
+}
+RT_HD void frame_store(Frame* f, const Frame& v) {
+  float4* q = reinterpret_cast<float4*>(f);
+  __stcg(q, make_float4(v.colour.x, v.colour.y, v.colour.z, __int_as_float(v.tag)));
+  __stcg(q + 1, make_float4(v.reflCol.x, v.reflCol.y, v.reflCol.z, 0.f));
+  __stcg(q + 2, make_float4(v.reflO.x, v.reflO.y, v.reflO.z, 0.f));
+  __stcg(q + 3, make_float4(v.reflD.x, v.reflD.y, v.reflD.z, 0.f));
+}
+#else
+RT_HD void frame_load_hot(const Frame* f, V3& colour, V3& reflCol, int& tag) { colour = f->colour; reflCol = f->reflCol; tag = f->tag; }
+RT_HD void frame_load_ray(const Frame* f, V3& reflO, V3& reflD) { reflO = f->reflO; reflD = f->reflD; }
+RT_HD void frame_store_head(Frame* f, V3 colour, int tag) { f->colour = colour; f->tag = tag; }
+RT_HD void frame_store(Frame* f, const Frame& v) { *f = v; }
+#endif
 
 struct Counters {         /* per-lane tallies, reduced per block at the end */
   uint32_t rays, shadow, containQ, containT, exactTests, samples;
@@ -567,30 +604,33 @@ RT_HD void shadow_geo(const Slot& s, const SceneView& sc, ShadowGeo& g) {
  * (raytracer.h:552-628).  Returns true when the sample is finished. */
 RT_HD bool unwind(Slot& s, Frame* stack, Counters& ctr, const Camera& cam) {
   if (s.top < 0) return true;
-  /* The frames live in local memory (an L2 round trip each) and the frames of consecutive levels are independent
+  /* The frames live in global memory (an L2 round trip each) and the frames of consecutive levels are independent
    * loads: the next level's words are requested while the current level is being combined, so popping k levels
    * costs one memory latency instead of k (ncu, 256 spheres: 6.5 % of all warp samples waited here). */
-  V3 col = stack[s.top].colour, rc = stack[s.top].reflCol;
-  int tag = stack[s.top].tag;
+  V3 col, rc, ro, rd;
+  int tag;
+  frame_load_hot(&stack[s.top], col, rc, tag);
+  frame_load_ray(&stack[s.top], ro, rd);        /* the top frame's reflected ray too: most pops launch it */
+  bool haveRay = true;
   for (;;) {
     const int lvl = s.top;
     V3 ncol = mk(0.f, 0.f, 0.f), nrc = ncol;
     int ntag = 0;
-    if (lvl > 0) { ncol = stack[lvl - 1].colour; nrc = stack[lvl - 1].reflCol; ntag = stack[lvl - 1].tag; }
+    if (lvl > 0) frame_load_hot(&stack[lvl - 1], ncol, nrc, ntag);
     --s.top;
     s.colour = vadd(s.result, col);
     if ((tag >> 16) == 1 && significant(rc)) {
       /* re-push as stage 2 (always fits: the slot was just vacated) */
       ++s.top;
-      Frame& f = stack[lvl];
       const int medium = tag & 0xFFFF;
-      f.colour = s.colour; f.tag = frame_tag(2, medium);
+      frame_store_head(&stack[lvl], s.colour, frame_tag(2, medium));
       s.result = s.colour;
       if (s.top < cam.S - 1) {
         /* reflected child, raytracer.h:602-611 */
-        s.rayD = f.reflD; s.rayI = rc; s.medium = medium;
+        if (!haveRay) frame_load_ray(&stack[lvl], ro, rd);
+        s.rayD = rd; s.rayI = rc; s.medium = medium;
         s.colour = mk(0.f, 0.f, 0.f);
-        set_trace_query(s, ctr, f.reflO, f.reflD);
+        set_trace_query(s, ctr, ro, rd);
         return false;
       }
       /* child push dropped (raytraceStack.h:52): the frame just written is popped again as stage 2 */
@@ -599,7 +639,7 @@ RT_HD bool unwind(Slot& s, Frame* stack, Counters& ctr, const Camera& cam) {
     }
     s.result = s.colour;
     if (lvl == 0) return true;
-    col = ncol; rc = nrc; tag = ntag;
+    col = ncol; rc = nrc; tag = ntag; haveRay = false;
   }
 }
 
@@ -680,11 +720,12 @@ RT_HD int after_contain(Slot& s, Frame* stack, Counters& ctr, const SceneView& s
   rc = vadd(rc, vscale(medA.w, mk(objB.x, objB.y, objB.z)));
   rc = vmul(s.rayI, rc);
 
-  /* suspend (always fits: depth <= S-1) */
+  /* suspend (always fits: depth <= S-1): the frame is built in registers and stored as one 64-byte chunk */
   ++s.top;
-  Frame& f = stack[s.top];
+  Frame f;
   f.colour = s.colour; f.tag = frame_tag(1, s.medium);
   f.reflCol = rc;
+  f.pad0 = f.pad1 = f.pad2 = 0;
   if (significant(rc)) {
     /* raytracer.h:817-842 */
     const float perp = ex_mul(2.f, vdot(s.rayD, s.Nrm));
@@ -694,6 +735,7 @@ RT_HD int after_contain(Slot& s, Frame* stack, Counters& ctr, const SceneView& s
   } else {
     f.reflD = mk(0.f, 0.f, 0.f); f.reflO = mk(0.f, 0.f, 0.f);
   }
+  frame_store(&stack[s.top], f);
   s.result = s.colour;                                   /* raytracer.h:538 */
   if (s.top < cam.S - 1) {
     s.rayD = rdir; s.rayI = rint; s.medium = target;

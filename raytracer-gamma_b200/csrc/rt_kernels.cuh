@@ -8,20 +8,23 @@
  * quantise_kernel  float4 framebuffer + max -> RGB8 (main.cpp:71-76)
  * assemble_rgb8_kernel  multi-GPU strip de-interleave
  *
- * State.  A sample in flight is a 24-word SLOT RECORD (the call being evaluated: result, colour, ray
- * direction / intensity, hit point, normal, matte sum, three header words).  The records of a CTA live
- * ON CHIP in shared memory, word-major (record word w of slot k of thread t at ((k*24+w)*256+t) words:
- * conflict-free), whenever they fit beside the filter records (SMEM_SLOTS; up to ~1 700 spheres with
- * three slots per lane); larger scenes and the accelerated mode keep them in local memory.  The
- * suspended calls (raytraceStack.h:13-68) are 13-word frames in local memory; a lane's census of its
- * slots' pending queries is one register.  The answer of a query (closest hit / occlusion bits /
- * container) never touches memory: the pass hands it to the state machine in registers.
+ * State.  A sample in flight is a 21-word SLOT RECORD (rt_core.cuh slot_pack: the call being evaluated — result,
+ * ray direction / intensity, hit point | ray origin, normal, matte sum | colour — and three header words).  The records
+ * of a CTA live ON CHIP in shared memory, word-major (record word w of slot k of thread t at ((k*21+w)*256+t) words:
+ * conflict-free), whenever they fit beside the filter records (SMEM_SLOTS; four slots per lane up to ~1 100 spheres,
+ * three up to ~1 700); larger scenes and the accelerated mode keep them in local memory.  The suspended calls
+ * (raytraceStack.h:13-68) are 64-byte frames in global memory, one chunk per frame (see trace_body); a lane's census
+ * of its slots' pending queries is one register.  The answer of a query (closest hit / occlusion bits / container)
+ * never touches memory: the pass hands it to the state machine in registers.
+ *
+ * Scheduling (all of it invisible in the frame): "Work order" below (every tile's first group, then the tiles those
+ * showed to be deep, then a sweep), and lockstep passes for short loops (trace_body).
  *
  * One pass of trace_kernel (per warp, all lanes converged throughout):
- *   refill   free slots take the next samples from a tile queue (one global atomicAdd
- *            per warp granule, __ballot_sync ranks the takers)
- *   vote     every lane reports which query kinds its slots are waiting on; the warp
- *            picks the kind that fills most lanes (__reduce_add_sync)
+ *   refill   every lane fills its first free slot from the warp's slice of work, round after round (one global
+ *            atomicAdd per 256-item slice of first groups, or one tile claim; __ballot_sync ranks the takers)
+ *   vote     every lane reports which query kinds its slots are waiting on; the warp — with lockstep
+ *            passes the CTA — picks the kind that fills most lanes (__reduce_add_sync)
  *   filter   the chosen kind's loop over ALL spheres, sphere records staged once per
  *            CTA into shared memory by a TMA bulk copy (cp.async.bulk + mbarrier) or
  *            read from the constant bank (launch parameter) for small scenes:
@@ -91,6 +94,7 @@ struct TraceParams {
   /* deep-tiles-first work order (lpt = 1): see "Work order" below */
   uint32_t lpt, sweepStep, deepAt;
   uint32_t lockstep;        /* 1: the warps of a CTA vote and start their passes together (see trace_body) */
+  Frame* frames;            /* [grid * RT_BLOCK * RT_SLOTS * cam.S] the threads' stacks of suspended calls */
   unsigned int* tileClaimed;/* [nTiles] 1 once the tile's other groups have been handed out or listed */
   unsigned int* deepList;   /* [nTiles] tile + 1 (0 = not written yet)                               */
   unsigned int* orderCtl;   /* list tail, list head, sweep cursor                                    */
@@ -1026,7 +1030,12 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   st.base = SMEM_SLOTS ? reinterpret_cast<uint32_t*>(smem_raw + 16 + filtBytes + list1Bytes +
                                                      RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)) + tid
                        : localSlots;
-  Frame stacks[NSLOTS * RT_MAX_STACK];
+  /* The suspended calls of this thread's slots: NSLOTS stacks of cam.S frames in GLOBAL memory, one 64-byte chunk per
+   * frame (Frame, rt_core.cuh).  A push dirties two 32-byte sectors and a pop reads one or two; in local memory —
+   * where the hardware interleaves the 32 lanes of a warp word by word — the same push dirtied up to thirteen
+   * sectors, because the lanes of a warp do not push together: 131 GB of DRAM traffic per 8K frame (ncu, round 2's
+   * first kernels) against 22 GB of frames actually written. */
+  Frame* const stacks = p.frames + ((size_t)(blockIdx.x * RT_BLOCK + tid) * NSLOTS) * (size_t)p.cam.S;
 #pragma unroll 1
   for (int k = 0; k < NSLOTS; ++k) { st.at(k, W_PIXEL) = RT_NO_PIXEL; st.at(k, W_HDR) = 0u; }
   uint32_t tags = 0u;   /* census kept in a register: byte k = kind | ndirs << 4 of slot k */
@@ -1195,7 +1204,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
       const int sv = r ? sv1 : sv0;
       if (!__any_sync(RT_FULL, sv >= 0)) continue;
       uint32_t deepPixel;
-      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * RT_MAX_STACK], ctr, laneMax, &sg, r ? a1 : a0, deepPixel);
+      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * p.cam.S], ctr, laneMax, &sg, r ? a1 : a0, deepPixel);
       if (sv >= 0) tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
       if (__any_sync(RT_FULL, deepPixel != RT_NO_PIXEL)) {
         if (deepPixel != RT_NO_PIXEL) mark_deep(p, tile_of_dst(p.wm, deepPixel));

@@ -54,6 +54,7 @@ struct rt_cuda_ctx {
   unsigned char* dRgb8 = nullptr; size_t rgbCap = 0;
   unsigned int* dWork = nullptr;     /* [0] queue head, [1] max bits */
   unsigned long long* dCounters = nullptr;
+  Frame* dFrames = nullptr; size_t framesCap = 0;       /* the threads' stacks of suspended calls (64 B per frame) */
   unsigned int* dOrder = nullptr; size_t orderCap = 0;   /* work-order state of a launch (rt_kernels.cuh "Work order") */
   void* dFlush = nullptr;
 
@@ -178,7 +179,7 @@ extern "C" void rt_cuda_destroy(rt_cuda_ctx* ctx) {
   if (ctx->stream) cudaStreamSynchronize(ctx->stream);
   if (ctx->copyStream) cudaStreamSynchronize(ctx->copyStream);
   cudaFree(ctx->dScene); cudaFree(ctx->dFb); cudaFree(ctx->dPacked); cudaFree(ctx->dRgb8); cudaFree(ctx->dSamples);
-  cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->dFlush); cudaFree(ctx->dOrder);
+  cudaFree(ctx->dWork); cudaFree(ctx->dCounters); cudaFree(ctx->dFlush); cudaFree(ctx->dOrder); cudaFree(ctx->dFrames);
   for (int i = 0; i < 2; ++i) {
     if (ctx->hChunk[i]) cudaFreeHost(ctx->hChunk[i]);
     if (ctx->evChunk[i]) cudaEventDestroy(ctx->evChunk[i]);
@@ -387,6 +388,10 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   if (ctx->order == 0 && (uint64_t)p.wm.nTiles * 32u < 4ull * grid * RT_BLOCK * RT_SLOTS) lpt = false;
   int rc = ensure_dev(ctx, ctx->dFb, ctx->fbCap, pixels ? pixels : 1);
   if (rc) { ctx->haveFrame = false; return rc; }
+  if (pixels && spp) {
+    rc = ensure_dev(ctx, ctx->dFrames, ctx->framesCap, (size_t)grid * RT_BLOCK * RT_SLOTS * (size_t)maxStack);
+    if (rc) { ctx->haveFrame = false; return rc; }
+  }
   const size_t orderWords = 32 + 2 * (size_t)p.wm.nTiles;
   if (lpt && pixels) {
     rc = ensure_dev(ctx, ctx->dOrder, ctx->orderCap, orderWords);
@@ -427,6 +432,7 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
   /* lockstep passes where the per-pass loop is short: few records (the accelerated mode loops over clusters) */
   const uint32_t loopRecords = accel ? ctx->ncPad : ctx->nPad;
   p.lockstep = (ctx->lockstep == 1 || (ctx->lockstep == 0 && loopRecords <= RT_LOCKSTEP_MAX_SPHERES)) ? 1u : 0u;
+  p.frames = ctx->dFrames;
   p.deepAt = ctx->deepAt ? (uint32_t)ctx->deepAt : RT_DEEP_AT;
   p.tileClaimed = p.deepList = p.orderCtl = nullptr;
   if (lpt) {

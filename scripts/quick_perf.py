@@ -11,8 +11,11 @@ print("ffma_peak TFLOP/s:", [round(r.ffma_peak(8192), 2) for _ in range(3)])
 cases = [
     ("default 1080p a1 s4", pkg.default_scene(), 1920, 1080, 1.0, 4, {}),
     ("synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {}),
+    ("synth512 4K a1 s8", pkg.synth_scene(512, 4), 3840, 2160, 1.0, 8, {}),
+    ("synth768 4K a1 s8", pkg.synth_scene(768, 4), 3840, 2160, 1.0, 8, {}),
     ("synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {}),
     ("synth1024 4K a2 s8", pkg.synth_scene(1024, 4), 3840, 2160, 2.0, 8, {}),
+    ("synth1024 8K a2 s8", pkg.synth_scene(1024, 4), 7680, 4320, 2.0, 8, {}),
     ("synth4096 2K a1 s8", pkg.synth_scene(4096, 4), 1920, 1080, 1.0, 8, {}),
     ("accel synth256 4K a1 s6", pkg.synth_scene(256, 4), 3840, 2160, 1.0, 6, {"accel": 2}),
     ("accel synth1024 4K a1 s8", pkg.synth_scene(1024, 4), 3840, 2160, 1.0, 8, {"accel": 1}),
