@@ -310,6 +310,11 @@ RT_HD bool contains_exact(float4_ g, V3 p) {
 
 /* ---- suspended calls -------------------------------------------------------- */
 #define RT_MAX_STACK 16
+#if defined(__CUDACC__)
+#define RT_FRAME_STRIDE 32     /* distance in frames between consecutive levels of one stack: the kernel keeps the 32 lanes' frames of a level side by side */
+#else
+#define RT_FRAME_STRIDE 1
+#endif
 #define RT_SHADOW_BATCH 4
 /* A suspended call: 13 words laid out as one 64-byte chunk = two 32-byte sectors.  Every pop reads the first
  * sector (colour, tag, reflection intensity: see unwind); only a pop that launches the reflected child reads the
@@ -331,26 +336,25 @@ Frame {
 RT_HD int frame_tag(int stage, int medium) { return (stage << 16) | medium; }
 RT_HD int frame_stage(const Frame& f) { return f.tag >> 16; }
 RT_HD int frame_medium(const Frame& f) { return f.tag & 0xFFFF; }
-/* Frame traffic: 16-byte vector accesses that bypass L1 (a frame is written once and read once, many passes later;
- * the small L1 left beside the slot records is better spent on the scene's geometry and material records). */
+/* Frame traffic: 16-byte vector accesses (ordinary caching: bypassing L1 with ld.cg / st.cg measured 0.5 % slower). */
 #if defined(__CUDA_ARCH__)
 RT_HD void frame_load_hot(const Frame* f, V3& colour, V3& reflCol, int& tag) {
-  const float4 a = __ldcg(reinterpret_cast<const float4*>(f)), b = __ldcg(reinterpret_cast<const float4*>(f) + 1);
+  const float4 a = *reinterpret_cast<const float4*>(f), b = *(reinterpret_cast<const float4*>(f) + 1);
   colour = mk(a.x, a.y, a.z); tag = __float_as_int(a.w); reflCol = mk(b.x, b.y, b.z);
 }
 RT_HD void frame_load_ray(const Frame* f, V3& reflO, V3& reflD) {
-  const float4 c = __ldcg(reinterpret_cast<const float4*>(f) + 2), d = __ldcg(reinterpret_cast<const float4*>(f) + 3);
+  const float4 c = *(reinterpret_cast<const float4*>(f) + 2), d = *(reinterpret_cast<const float4*>(f) + 3);
   reflO = mk(c.x, c.y, c.z); reflD = mk(d.x, d.y, d.z);
 }
 RT_HD void frame_store_head(Frame* f, V3 colour, int tag) {
-  __stcg(reinterpret_cast<float4*>(f), make_float4(colour.x, colour.y, colour.z, __int_as_float(tag)));
+  *reinterpret_cast<float4*>(f) = make_float4(colour.x, colour.y, colour.z, __int_as_float(tag));
 }
 RT_HD void frame_store(Frame* f, const Frame& v) {
   float4* q = reinterpret_cast<float4*>(f);
-  __stcg(q, make_float4(v.colour.x, v.colour.y, v.colour.z, __int_as_float(v.tag)));
-  __stcg(q + 1, make_float4(v.reflCol.x, v.reflCol.y, v.reflCol.z, 0.f));
-  __stcg(q + 2, make_float4(v.reflO.x, v.reflO.y, v.reflO.z, 0.f));
-  __stcg(q + 3, make_float4(v.reflD.x, v.reflD.y, v.reflD.z, 0.f));
+  q[0] = make_float4(v.colour.x, v.colour.y, v.colour.z, __int_as_float(v.tag));
+  q[1] = make_float4(v.reflCol.x, v.reflCol.y, v.reflCol.z, 0.f);
+  q[2] = make_float4(v.reflO.x, v.reflO.y, v.reflO.z, 0.f);
+  q[3] = make_float4(v.reflD.x, v.reflD.y, v.reflD.z, 0.f);
 }
 #else
 RT_HD void frame_load_hot(const Frame* f, V3& colour, V3& reflCol, int& tag) { colour = f->colour; reflCol = f->reflCol; tag = f->tag; }
@@ -609,25 +613,23 @@ RT_HD bool unwind(Slot& s, Frame* stack, Counters& ctr, const Camera& cam) {
    * costs one memory latency instead of k (ncu, 256 spheres: 6.5 % of all warp samples waited here). */
   V3 col, rc, ro, rd;
   int tag;
-  frame_load_hot(&stack[s.top], col, rc, tag);
-  frame_load_ray(&stack[s.top], ro, rd);        /* the top frame's reflected ray too: most pops launch it */
-  bool haveRay = true;
+  frame_load_hot(&stack[s.top * RT_FRAME_STRIDE], col, rc, tag);
   for (;;) {
     const int lvl = s.top;
     V3 ncol = mk(0.f, 0.f, 0.f), nrc = ncol;
     int ntag = 0;
-    if (lvl > 0) frame_load_hot(&stack[lvl - 1], ncol, nrc, ntag);
+    if (lvl > 0) frame_load_hot(&stack[(lvl - 1) * RT_FRAME_STRIDE], ncol, nrc, ntag);
     --s.top;
     s.colour = vadd(s.result, col);
     if ((tag >> 16) == 1 && significant(rc)) {
       /* re-push as stage 2 (always fits: the slot was just vacated) */
       ++s.top;
       const int medium = tag & 0xFFFF;
-      frame_store_head(&stack[lvl], s.colour, frame_tag(2, medium));
+      frame_store_head(&stack[lvl * RT_FRAME_STRIDE], s.colour, frame_tag(2, medium));
       s.result = s.colour;
       if (s.top < cam.S - 1) {
         /* reflected child, raytracer.h:602-611 */
-        if (!haveRay) frame_load_ray(&stack[lvl], ro, rd);
+        frame_load_ray(&stack[lvl * RT_FRAME_STRIDE], ro, rd);
         s.rayD = rd; s.rayI = rc; s.medium = medium;
         s.colour = mk(0.f, 0.f, 0.f);
         set_trace_query(s, ctr, ro, rd);
@@ -639,7 +641,7 @@ RT_HD bool unwind(Slot& s, Frame* stack, Counters& ctr, const Camera& cam) {
     }
     s.result = s.colour;
     if (lvl == 0) return true;
-    col = ncol; rc = nrc; tag = ntag; haveRay = false;
+    col = ncol; rc = nrc; tag = ntag;
   }
 }
 
@@ -735,7 +737,7 @@ RT_HD int after_contain(Slot& s, Frame* stack, Counters& ctr, const SceneView& s
   } else {
     f.reflD = mk(0.f, 0.f, 0.f); f.reflO = mk(0.f, 0.f, 0.f);
   }
-  frame_store(&stack[s.top], f);
+  frame_store(&stack[s.top * RT_FRAME_STRIDE], f);
   s.result = s.colour;                                   /* raytracer.h:538 */
   if (s.top < cam.S - 1) {
     s.rayD = rdir; s.rayI = rint; s.medium = target;

@@ -1031,11 +1031,14 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
                                                      RT_LIST_MAX * RT_BLOCK * sizeof(unsigned short)) + tid
                        : localSlots;
   /* The suspended calls of this thread's slots: NSLOTS stacks of cam.S frames in GLOBAL memory, one 64-byte chunk per
-   * frame (Frame, rt_core.cuh).  A push dirties two 32-byte sectors and a pop reads one or two; in local memory —
-   * where the hardware interleaves the 32 lanes of a warp word by word — the same push dirtied up to thirteen
-   * sectors, because the lanes of a warp do not push together: 131 GB of DRAM traffic per 8K frame (ncu, round 2's
-   * first kernels) against 22 GB of frames actually written. */
-  Frame* const stacks = p.frames + ((size_t)(blockIdx.x * RT_BLOCK + tid) * NSLOTS) * (size_t)p.cam.S;
+   * frame (Frame, rt_core.cuh), the 32 lanes' frames of one (slot, depth) side by side:
+   *     frame (slot, depth) of this lane at ((warp * NSLOTS + slot) * S + depth) * 32 + lane.
+   * A push dirties two 32-byte sectors and a pop reads one or two.  In local memory — where the hardware interleaves
+   * the lanes of a warp word by word — the same push dirtied up to thirteen sectors, because the lanes of a warp do
+   * not push together: 140 GB of DRAM traffic per 8K frame against 33 GB like this (ncu).  With every lane's stack
+   * in its own 2 KB region instead of this warp-wise arrangement the kernel was 1 % slower (one L1 line per lane and
+   * access; here two lanes share a line). */
+  Frame* const stacks = p.frames + ((size_t)((blockIdx.x * RT_BLOCK + tid) >> 5) * NSLOTS) * (size_t)p.cam.S * 32u + lane;
 #pragma unroll 1
   for (int k = 0; k < NSLOTS; ++k) { st.at(k, W_PIXEL) = RT_NO_PIXEL; st.at(k, W_HDR) = 0u; }
   uint32_t tags = 0u;   /* census kept in a register: byte k = kind | ndirs << 4 of slot k */
@@ -1204,7 +1207,7 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
       const int sv = r ? sv1 : sv0;
       if (!__any_sync(RT_FULL, sv >= 0)) continue;
       uint32_t deepPixel;
-      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * p.cam.S], ctr, laneMax, &sg, r ? a1 : a0, deepPixel);
+      const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * p.cam.S * RT_FRAME_STRIDE], ctr, laneMax, &sg, r ? a1 : a0, deepPixel);
       if (sv >= 0) tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
       if (__any_sync(RT_FULL, deepPixel != RT_NO_PIXEL)) {
         if (deepPixel != RT_NO_PIXEL) mark_deep(p, tile_of_dst(p.wm, deepPixel));
