@@ -19,7 +19,7 @@ using namespace rtg;
 #ifndef RT_DEFAULT_SLOTS
 #define RT_DEFAULT_SLOTS 4
 #endif
-#define RT_LOCKSTEP_MAX_SPHERES 512u  /* lockstep passes up to this many filter records (rt_kernels.cuh trace_body) */
+#define RT_LOCKSTEP_MAX_SPHERES 640u  /* lockstep passes up to this many filter records (rt_kernels.cuh trace_body): 12 % faster at 512, 2 % slower at 768 */
 #define RT_COPY_CHUNK (8u << 20)     /* pageable readback: D2H and the host memcpy alternate over two pinned chunks */
 #define RT_FLUSH_BYTES (256u << 20)  /* rt_cuda_flush_l2: larger than the 126 MB L2 */
 

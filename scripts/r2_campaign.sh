@@ -1,5 +1,5 @@
 #!/bin/bash
-# Round-2 measurement campaign on N GPUs of one box: usage r2_campaign.sh <N> ["list of gpu counts to bench"]
+# Round-2 measurement campaign on N GPUs of one box: usage r2_campaign.sh <N> ["list of gpu counts to bench"] [nosweep] [c4only]
 # -> gpurun_out/campaign_n<N>/ (bench lines for config 4 and config 3, config-5 sweep, host program, GPU tests)
 set -u
 N=$1; counts=${2:-$N}
@@ -30,7 +30,7 @@ if [ $N -gt 1 ]; then
   timeout 1200 python -m pytest tests -m gpu -x -q -k "multi or strips" > $O/pytest_multi.txt 2>&1; echo "pytest rc=$?"; tail -3 $O/pytest_multi.txt
 fi
 for n in $counts; do run_bench $n config4; done
-for n in $counts; do run_bench $n config3; done
+[ "${4:-}" = "c4only" ] || for n in $counts; do run_bench $n config3; done
 if [ $N -eq 1 ]; then
   for wl in config1 config2; do run_bench 1 $wl; done
   timeout 600 python bench.py --impl reference --steps 3 --warmup 1 > $O/bench_reference_arm.json 2> $O/bench_reference_arm.err; echo "reference arm rc=$?"
