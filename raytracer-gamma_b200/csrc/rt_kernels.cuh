@@ -157,17 +157,20 @@ __device__ __forceinline__ void tma_bulk_g2s(void* dst, const void* src, uint32_
  * multi-consumer array in global memory (entries are written after the tail has moved: a consumer waits for
  * the entry it has claimed); a tile is claimed — by the deep trigger or by the sweep — with one atomicExch
  * on tileClaimed[].  A warp is done when the sweep has passed the last tile, the list is empty and its own
- * samples are finished; a tile marked deep after that is worked off by the warp that marked it.  The frame
+ * samples are finished; a warp that lists a tile looks at the list again afterwards, so a tile listed while the
+ * others are leaving is worked off by the warp that listed it.  The frame
  * does not depend on the order (samples are independent, main.cpp:439). */
 __device__ __forceinline__ unsigned ld_volatile(const unsigned* p) { return *reinterpret_cast<const volatile unsigned*>(p); }
 enum { ORD_TAIL = 0, ORD_HEAD = 1, ORD_SWEEP = 2 };     /* orderCtl words */
 
 /* A first-group sample of `tile` has just reached RT_DEEP_AT queries.  Out of line, called from converged code. */
-__device__ __noinline__ void mark_deep(const TraceParams& p, uint32_t tile) {
+__device__ __noinline__ bool mark_deep(const TraceParams& p, uint32_t tile) {
   if (atomicExch(&p.tileClaimed[tile], 1u) == 0u) {
     const unsigned pos = atomicAdd(&p.orderCtl[ORD_TAIL], 1u);
     atomicExch(&p.deepList[pos], tile + 1u);
+    return true;          /* listed: the caller makes sure somebody (itself, at the latest) takes it */
   }
+  return false;
 }
 /* Next tiles for this warp (whole warp calls): up to RT_SWEEP_STEP tiles; bit l of the result = lane l holds a tile in
  * *mine.  0 with *allOut = nothing is left to hand out; 0 without = the sweep step found only claimed tiles (call again). */
@@ -1210,7 +1213,11 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
       const uint32_t tg = advance_slot(p, st, sv, &stacks[(sv < 0 ? 0 : sv) * p.cam.S * RT_FRAME_STRIDE], ctr, laneMax, &sg, r ? a1 : a0, deepPixel);
       if (sv >= 0) tags = (tags & ~(0xFFu << (8 * sv))) | (tg << (8 * sv));
       if (__any_sync(RT_FULL, deepPixel != RT_NO_PIXEL)) {
-        if (deepPixel != RT_NO_PIXEL) mark_deep(p, tile_of_dst(p.wm, deepPixel));
+        bool listed = false;
+        if (deepPixel != RT_NO_PIXEL) listed = mark_deep(p, tile_of_dst(p.wm, deepPixel));
+        /* a warp that had already found nothing left to hand out looks again: the tile it has just listed must not
+         * depend on another warp still being there to take it */
+        if (__any_sync(RT_FULL, listed)) queueDry = false;
       }
     }
     RT_TICK(4);
