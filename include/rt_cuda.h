@@ -157,8 +157,9 @@ int rt_cuda_flush_l2(rt_cuda_ctx* ctx);
  * "order" 0 auto (= 1 on frames large enough for it to pay, else 2) | 1: every tile's first group, then the tiles it showed to be deep, then the rest (so that a
  *   launch does not end on a few warps working off 100-query chains) | 2: tiles in scanline order;
  *   "deep_at" / "sweep_step": its tuning (0 = default: 24 queries / at most one tile per claim);
- * "lockstep" 0 auto (on where the per-pass loop is short: <= 640 records) | 1 on | 2 off: the warps of a CTA vote and
- *   start their passes together, which keeps the instruction working set of an SM inside its instruction cache;
+ * "lockstep" 0 auto (by the number of filter records: the whole CTA up to 384, halves of it up to 896, off beyond) |
+ *   1 whole CTA | 2 off | 3 half-CTAs: the warps of a group vote and start their passes together, which keeps the
+ *   instruction working set of an SM inside its instruction cache;
  * "slot_mode" 0 auto (slot records in shared memory whenever two CTAs per SM still fit) | 1 shared | 2 local;
  * (development builds, -DRT_DEV_VARIANTS: "slots" 3 | 4 for the local-memory kernel);
  * "accel" 0 off | 1 = two-level cluster filter where it pays (>= 768 spheres) | 2 = from 32 spheres.

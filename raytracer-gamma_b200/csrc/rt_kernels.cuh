@@ -78,6 +78,7 @@ namespace rtg {
 #ifndef RT_SHADOW_INLINE_NORM
 #define RT_SHADOW_INLINE_NORM 0  /* the four normalisations of a shadow batch inline (they overlap) rather than out of line */
 #endif
+#define RT_LOCK_WARPS_MIN 4       /* smallest group of warps that vote and start their passes together under lockstep */
 #define RT_SLOTS 4               /* slots per lane (3 in shared memory when 4 do not fit beside the filter records) */
 
 struct TraceParams {
@@ -93,7 +94,7 @@ struct TraceParams {
   uint32_t total1, chunk;   /* items the queue head hands out (all of them, or the tiles' first groups), queue granule */
   /* deep-tiles-first work order (lpt = 1): see "Work order" below */
   uint32_t lpt, sweepStep, deepAt;
-  uint32_t lockstep;        /* 1: the warps of a CTA vote and start their passes together (see trace_body) */
+  uint32_t lockstep;        /* 0 | 8 | 4: this many warps of a CTA vote and start their passes together (see trace_body) */
   Frame* frames;            /* [grid * RT_BLOCK * RT_SLOTS * cam.S] the threads' stacks of suspended calls */
   unsigned int* tileClaimed;/* [nTiles] 1 once the tile's other groups have been handed out or listed */
   unsigned int* deepList;   /* [nTiles] tile + 1 (0 = not written yet)                               */
@@ -1056,8 +1057,9 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
   bool segBucket = false, headDry = false;
   uint32_t entMine = 0, entMask = 0;     /* tiles the warp has claimed and not started: bit l = lane l holds one */
   bool queueDry = false;                 /* nothing left to hand out: the warp finishes what it has in flight */
-  __shared__ unsigned sVote[3][8];       /* lockstep passes: the CTA's census of a round (nT, nS, nC, ndMax, warps not finished) */
-  if (tid < 24) (&sVote[0][0])[tid] = 0u;
+  /* lockstep passes: the census of a round (nT, nS, nC, ndMax, warps not finished) of each group of p.lockstep warps */
+  __shared__ unsigned sVote[RT_BLOCK / 32 / RT_LOCK_WARPS_MIN][3][8];
+  if (tid < (RT_BLOCK / 32 / RT_LOCK_WARPS_MIN) * 24) (&sVote[0][0][0])[tid] = 0u;
   __syncthreads();
   int voteBuf = 0;
 
@@ -1144,14 +1146,15 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
     unsigned nC = __reduce_add_sync(RT_FULL, (unsigned)((c0 >= 0) + (c1 >= 0)));
     int ndMax = __reduce_max_sync(RT_FULL, nd);
     if (p.lockstep) {
-      /* Lockstep passes (small scenes): the warps of a CTA vote TOGETHER and start every pass together (one barrier
-       * per pass), so that at any time a CTA executes one phase of one pass kind — the instruction working set of
+      /* Lockstep passes (small scenes): the warps of a CTA — or of each half of it — vote TOGETHER and start every pass
+       * together (one named barrier per pass), so that at any time a CTA executes one phase of one pass kind — the instruction working set of
        * an SM is two phases instead of sixteen.  The kernel is ~80 KB of code against a 32 KB instruction cache:
        * at 256 spheres 44 % of the warp samples are instruction-fetch stalls without it and 3 % with it (ncu,
        * profiles/r2).  Equal kinds also mean equal loop lengths, so the barrier costs little; a warp with nothing
        * of the CTA's kind sits the pass out.  Large scenes run free: their passes are long loops out of a 3 KB
        * body, and the common vote would cost them fill. */
-      unsigned* vt = sVote[voteBuf];
+      const unsigned grp = (tid >> 5) / p.lockstep;        /* p.lockstep = warps per group: 8 (the CTA) or 4 */
+      unsigned* vt = sVote[grp][voteBuf];
       const bool idle = (nT | nS | nC) == 0u;
       if (lane == 0) {
         if (nT) atomicAdd(&vt[0], nT);
@@ -1160,11 +1163,11 @@ __device__ __forceinline__ void trace_body(const TraceParams& p, const ConstReco
         if (ndMax) atomicMax(&vt[3], (unsigned)ndMax);
         if (!(idle && queueDry)) atomicAdd(&vt[4], 1u);
       }
-      __syncthreads();
+      asm volatile("bar.sync %0, %1;" ::"r"(1u + grp), "r"(32u * p.lockstep) : "memory");
       const unsigned cT = vt[0], cS = vt[1], cC = vt[2], cNd = vt[3], cLive = vt[4];
       /* three buffers in rotation: clear the PREVIOUS round's (every read of it came before the barrier above, its
        * next use comes after the next barrier) */
-      if (tid < 5u) sVote[(voteBuf + 2) % 3][tid] = 0u;
+      if ((tid & (32u * p.lockstep - 1u)) < 5u) sVote[grp][(voteBuf + 2) % 3][tid & 7u] = 0u;
       voteBuf = (voteBuf + 1) % 3;
       if (cLive == 0u) break;
       if ((cT | cS | cC) == 0u) continue;

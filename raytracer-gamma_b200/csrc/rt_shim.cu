@@ -19,7 +19,8 @@ using namespace rtg;
 #ifndef RT_DEFAULT_SLOTS
 #define RT_DEFAULT_SLOTS 4
 #endif
-#define RT_LOCKSTEP_MAX_SPHERES 640u  /* lockstep passes up to this many filter records (rt_kernels.cuh trace_body): 12 % faster at 512, 2 % slower at 768 */
+#define RT_LOCKSTEP_CTA_MAX 384u      /* lockstep passes of the whole CTA up to this many filter records (rt_kernels.cuh trace_body) */
+#define RT_LOCKSTEP_MAX_SPHERES 896u  /* ... of half-CTAs up to this many; free-running warps beyond */
 #define RT_COPY_CHUNK (8u << 20)     /* pageable readback: D2H and the host memcpy alternate over two pinned chunks */
 #define RT_FLUSH_BYTES (256u << 20)  /* rt_cuda_flush_l2: larger than the 126 MB L2 */
 
@@ -77,7 +78,7 @@ struct rt_cuda_ctx {
   int staging = 0, noFilter = 0, blocksPerSM = 0, slots = 0;
   int order = 0;                   /* 0 auto (= 1) | 1: deep tiles first | 2: tiles in scanline order */
   int sweepStep = 0, deepAt = 0;   /* work-order tuning (0 = default) */
-  int lockstep = 0;                /* 0 auto (scenes of <= RT_LOCKSTEP_MAX_SPHERES records) | 1 on | 2 off */
+  int lockstep = 0;                /* 0 auto (by the number of filter records) | 1 whole CTA | 2 off | 3 half-CTAs */
   int slotMode = 0;                /* 0 auto | 1 slot records in shared memory | 2 in local memory */
   int accel = 0;                   /* 1: two-level cluster filter (optional accelerated mode) */
   uint32_t nc = 0, ncPad = 0;
@@ -224,7 +225,7 @@ extern "C" int rt_cuda_set_option(rt_cuda_ctx* ctx, const char* key, long value)
   if (!strcmp(key, "accel")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->accel = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "blocks_per_sm")) { if (value < 0 || value > 8) return RT_CUDA_ERR_INVALID_ARG; ctx->blocksPerSM = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "order")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->order = (int)value; return RT_CUDA_OK; }
-  if (!strcmp(key, "lockstep")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->lockstep = (int)value; return RT_CUDA_OK; }
+  if (!strcmp(key, "lockstep")) { if (value < 0 || value > 3) return RT_CUDA_ERR_INVALID_ARG; ctx->lockstep = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "sweep_step")) { if (value < 0 || value > 32) return RT_CUDA_ERR_INVALID_ARG; ctx->sweepStep = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "deep_at")) { if (value < 0 || value > RT_COUNT_MAX) return RT_CUDA_ERR_INVALID_ARG; ctx->deepAt = (int)value; return RT_CUDA_OK; }
   if (!strcmp(key, "slot_mode")) { if (value < 0 || value > 2) return RT_CUDA_ERR_INVALID_ARG; ctx->slotMode = (int)value; return RT_CUDA_OK; }
@@ -429,9 +430,14 @@ extern "C" int rt_cuda_render_strips(rt_cuda_ctx* ctx, unsigned width, unsigned 
    * 14.4 ms at 256 spheres / 4K with up to 8: neighbouring tiles are equally deep, and a claim of several lands all of
    * them on one warp */
   p.sweepStep = ctx->sweepStep ? (uint32_t)ctx->sweepStep : 1u;
-  /* lockstep passes where the per-pass loop is short: few records (the accelerated mode loops over clusters) */
+  /* lockstep passes where the per-pass loop is short (the accelerated mode loops over clusters): the whole CTA up to
+   * RT_LOCKSTEP_CTA_MAX records, halves of it up to RT_LOCKSTEP_MAX_SPHERES (measured at 4K, profiles/r2/ab_lockstep_groups.txt:
+   * 256 records 13.8 ms with 8 warps, 14.2 with 4, 18.5 free; 512: 26.0 / 24.9 / 30.1; 768: 42.3 / 41.4 / 43.5; 1 024: 201.7 / 193.5 / 192.0) */
+  const uint32_t ctaMax = accel ? 64u : RT_LOCKSTEP_CTA_MAX, halfMax = accel ? 512u : RT_LOCKSTEP_MAX_SPHERES;   /* accelerated mode: cluster records
+      (1 024 spheres = 128 clusters: 40.5 ms with 8 warps, 38.2 with 4, 48.9 free; 256 spheres = 32 clusters: 15.1 / 16.4 / 22.1) */
   const uint32_t loopRecords = accel ? ctx->ncPad : ctx->nPad;
-  p.lockstep = (ctx->lockstep == 1 || (ctx->lockstep == 0 && loopRecords <= RT_LOCKSTEP_MAX_SPHERES)) ? 1u : 0u;
+  p.lockstep = (ctx->lockstep == 1) ? 8u : (ctx->lockstep == 3) ? 4u : (ctx->lockstep == 2) ? 0u
+             : (loopRecords <= ctaMax) ? 8u : (loopRecords <= halfMax) ? 4u : 0u;
   p.frames = ctx->dFrames;
   p.deepAt = ctx->deepAt ? (uint32_t)ctx->deepAt : RT_DEEP_AT;
   p.tileClaimed = p.deepList = p.orderCtl = nullptr;

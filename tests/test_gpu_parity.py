@@ -136,7 +136,7 @@ def test_work_order_and_lockstep_variants_agree(pkg, orc_mod, oracle, gpu):
     sph, lgt = pkg.synth_scene(300, 4, seed=5)
     for W, H, alias in ((601, 403, 1.0), (320, 200, 2.0), (97, 61, 3.0)):
         ref, ctr = oracle.render(sph, lgt, W, H, -4.0, alias, 8)
-        for opts in ({}, {"order": 1}, {"order": 2}, {"order": 1, "lockstep": 1}, {"order": 1, "lockstep": 2}, {"order": 2, "lockstep": 1},
+        for opts in ({}, {"order": 1}, {"order": 2}, {"order": 1, "lockstep": 1}, {"order": 1, "lockstep": 2}, {"order": 1, "lockstep": 3}, {"lockstep": 3}, {"order": 2, "lockstep": 1},
                      {"order": 1, "sweep_step": 3, "deep_at": 6}, {"order": 1, "deep_at": 2, "sweep_step": 8, "lockstep": 2},
                      {"order": 1, "slot_mode": 2, "deep_at": 4}, {"order": 1, "accel": 2, "deep_at": 3}):
             fb, _, st = _render(gpu, sph, lgt, W, H, -4.0, alias, 8, **opts)
