@@ -132,7 +132,7 @@ def kernel_phase(l):
         if "---- per-warp reductions" in t: return "kernel: epilogue"
         if "---- advance the served slots" in t: return "kernel: advance glue"
         if "---- vote ----" in t: return "kernel: vote + dispatch"
-        if "---- refill ----" in t: return "kernel: refill"
+        if "---- refill" in t: return "kernel: refill"
         if "void trace_body(" in t: return "kernel: prologue"
     return "kernel: other"
 
