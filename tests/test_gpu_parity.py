@@ -144,6 +144,36 @@ def test_work_order_and_lockstep_variants_agree(pkg, orc_mod, oracle, gpu):
             assert st["rays"] == ctr["rays"] and st["samples"] == ctr["samples"], (W, H, alias, opts)
 
 
+def test_work_order_protocol_stress(pkg, orc_mod, gpu):
+    """The deep list and the sweep hand every tile out exactly once whatever the timing: random frame shapes (ragged
+    tiles, strips, 1 and 4 spp) with the deep trigger at 1-3 queries (every tile is listed by its first samples), claims
+    of 1-8 tiles and every lockstep mode, against the scanline order of the same frame: same bits, same ray and sample
+    counts."""
+    rng = np.random.default_rng(7)
+    sph, lgt = pkg.synth_scene(96, 3, seed=9)
+    for it in range(24):
+        W, H = int(rng.integers(9, 400)), int(rng.integers(5, 300))
+        alias = float(rng.choice([1.0, 2.0]))
+        strips = (int(rng.integers(1, 9)), 0, 1) if it % 3 else (4, int(rng.integers(0, 3)), 3)
+        opts = {"order": 1, "deep_at": int(rng.integers(1, 4)), "sweep_step": int(rng.integers(1, 9)), "lockstep": int(rng.integers(0, 4))}
+        frames = []
+        for o in ({"order": 2}, opts):
+            for k, v in o.items():
+                gpu.set_option(k, v)
+            gpu.upload_scene(sph, lgt)
+            if it % 3:
+                gpu.render(W, H, -4.0, alias, 8)
+            else:
+                gpu.render_strips(W, H, -4.0, alias, 8, *strips)
+            fb, _ = gpu.readback()
+            st = gpu.stats()
+            for k in o:
+                gpu.set_option(k, 0)
+            frames.append((orc_mod.canon(fb), st["rays"], st["samples"]))
+        assert np.array_equal(frames[0][0], frames[1][0]), (it, W, H, alias, strips, opts)
+        assert frames[0][1:] == frames[1][1:], (it, W, H, alias, strips, opts)
+
+
 def test_edge_cases(pkg, orc_mod, oracle, gpu):
     sph, lgt = pkg.default_scene()
     # empty scene, no lights, 1-pixel-high and non-tile-multiple frames, sub-unit alias
